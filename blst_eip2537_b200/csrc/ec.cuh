@@ -1,0 +1,170 @@
+// ec.cuh -- K2: field-generic short-Weierstrass (a = 0) point arithmetic for E(Fp) and E'(Fp2).
+//
+// Replaces blst_p{1,2}_add_or_double (/root/reference/src/eip2537.c:183,197,605,693 and
+// :237,251,894,983), blst_p{1,2}_from_affine / _to_affine (:598,610,698 / :887,899,988) and
+// blst_p{1,2}_affine_on_curve (:336, :397).  Accumulators use extended Jacobian "XYZZ"
+// coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2): mixed add 8M+2S, full add 12M+2S,
+// double 6M+3S.  All exceptional cases are handled exactly (P == Q doubles, P == -Q gives
+// infinity, either operand infinite) because MULTIEXP inputs are adversarial: no subgroup
+// check is applied to them (eip2537.c:340, :401), repeated points and P/-P pairs are legal.
+// E(Fp) and E'(Fp2) have odd order, so y = 0 never occurs on-curve and doubling needs no
+// 2-torsion case.
+#pragma once
+#include "fp.cuh"
+
+namespace b200 {
+
+template <class F>
+struct Affine {   // (0,0) encodes infinity, as the reference's blst_p*_affine does
+  F x, y;
+};
+template <class F>
+struct XYZZ {     // infinity <=> zz == 0
+  F x, y, zz, zzz;
+};
+
+template <class F>
+B200_HD bool is_inf(const Affine<F>& a) { return is_zero(a.x) && is_zero(a.y); }
+template <class F>
+B200_HD bool is_inf(const XYZZ<F>& a) { return is_zero(a.zz); }
+
+template <class F>
+B200_HD XYZZ<F> xyzz_inf() {
+  XYZZ<F> r;
+  r.x = FieldOps<F>::zero(); r.y = FieldOps<F>::zero(); r.zz = FieldOps<F>::zero(); r.zzz = FieldOps<F>::zero();
+  return r;
+}
+template <class F>
+B200_HD XYZZ<F> xyzz_from_affine(const Affine<F>& a) {
+  XYZZ<F> r;
+  r.x = a.x; r.y = a.y;
+  if (is_inf(a)) { r.zz = FieldOps<F>::zero(); r.zzz = FieldOps<F>::zero(); }
+  else           { r.zz = FieldOps<F>::one();  r.zzz = FieldOps<F>::one(); }
+  return r;
+}
+template <class F>
+B200_HD Affine<F> affine_neg(const Affine<F>& a) { Affine<F> r; r.x = a.x; r.y = neg(a.y); return r; }
+template <class F>
+B200_HD XYZZ<F> xyzz_neg(const XYZZ<F>& a) { XYZZ<F> r = a; r.y = neg(a.y); return r; }
+
+// y^2 == x^3 + b ; caller has already excluded the (0,0) infinity encoding
+template <class F>
+B200_HD bool affine_on_curve(const Affine<F>& a) {
+  F lhs = sqr(a.y);
+  F rhs = add(mul(sqr(a.x), a.x), FieldOps<F>::curve_b());
+  return eq(lhs, rhs);
+}
+
+// 2*(x,y) for a finite affine point -> XYZZ   (mdbl-2008-s-1)
+template <class F>
+B200_HD_NI XYZZ<F> xyzz_dbl_affine(const Affine<F>& a) {
+  XYZZ<F> r;
+  F u = dbl(a.y);
+  F v = sqr(u);
+  F w = mul(u, v);
+  F s = mul(a.x, v);
+  F x2 = sqr(a.x);
+  F m = add(dbl(x2), x2);
+  r.x = sub(sqr(m), dbl(s));
+  r.y = sub(mul(m, sub(s, r.x)), mul(w, a.y));
+  r.zz = v;
+  r.zzz = w;
+  return r;
+}
+
+// 2*P   (dbl-2008-s-1)
+template <class F>
+B200_HD_NI XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
+  if (is_inf(p)) return p;
+  XYZZ<F> r;
+  F u = dbl(p.y);
+  F v = sqr(u);
+  F w = mul(u, v);
+  F s = mul(p.x, v);
+  F x2 = sqr(p.x);
+  F m = add(dbl(x2), x2);
+  r.x = sub(sqr(m), dbl(s));
+  r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
+  r.zz = mul(v, p.zz);
+  r.zzz = mul(w, p.zzz);
+  return r;
+}
+
+// acc += q (q affine, may be infinity)   (madd-2008-s)
+template <class F>
+B200_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q) {
+  if (is_inf(q)) return;
+  if (is_inf(acc)) { acc = xyzz_from_affine(q); return; }
+  F u2 = mul(q.x, acc.zz);
+  F s2 = mul(q.y, acc.zzz);
+  F p = sub(u2, acc.x);
+  F r = sub(s2, acc.y);
+  if (is_zero(p)) {
+    if (is_zero(r)) acc = xyzz_dbl_affine(q);   // same point: double
+    else            acc = xyzz_inf<F>();        // opposite points cancel
+    return;
+  }
+  F pp = sqr(p);
+  F ppp = mul(p, pp);
+  F qq = mul(acc.x, pp);
+  F x3 = sub(sub(sqr(r), ppp), dbl(qq));
+  acc.y = sub(mul(r, sub(qq, x3)), mul(acc.y, ppp));
+  acc.x = x3;
+  acc.zz = mul(acc.zz, pp);
+  acc.zzz = mul(acc.zzz, ppp);
+}
+
+// acc += q (both XYZZ)   (add-2008-s)
+template <class F>
+B200_HD_NI void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
+  if (is_inf(q)) return;
+  if (is_inf(acc)) { acc = q; return; }
+  F u1 = mul(acc.x, q.zz);
+  F u2 = mul(q.x, acc.zz);
+  F s1 = mul(acc.y, q.zzz);
+  F s2 = mul(q.y, acc.zzz);
+  F p = sub(u2, u1);
+  F r = sub(s2, s1);
+  if (is_zero(p)) {
+    if (is_zero(r)) acc = xyzz_dbl(acc);
+    else            acc = xyzz_inf<F>();
+    return;
+  }
+  F pp = sqr(p);
+  F ppp = mul(p, pp);
+  F qq = mul(u1, pp);
+  F x3 = sub(sub(sqr(r), ppp), dbl(qq));
+  acc.y = sub(mul(r, sub(qq, x3)), mul(s1, ppp));
+  acc.x = x3;
+  acc.zz = mul(mul(acc.zz, q.zz), pp);
+  acc.zzz = mul(mul(acc.zzz, q.zzz), ppp);
+}
+
+// x = X/ZZ, y = Y/ZZZ with one inversion; infinity -> (0,0)
+template <class F>
+B200_HD_NI Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
+  Affine<F> r;
+  if (is_inf(p)) { r.x = FieldOps<F>::zero(); r.y = FieldOps<F>::zero(); return r; }
+  F i = inv(mul(p.zz, p.zzz));
+  r.x = mul(p.x, mul(i, p.zzz));
+  r.y = mul(p.y, mul(i, p.zz));
+  return r;
+}
+
+// k * P by double-and-add, k given as little-endian 32-bit words, `nbits` significant bits
+template <class F>
+B200_HD_NI XYZZ<F> xyzz_scalar_mul(const Affine<F>& p, const uint32_t* k, int nbits) {
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (int i = nbits - 1; i >= 0; i--) {
+    acc = xyzz_dbl(acc);
+    if ((k[i >> 5] >> (i & 31)) & 1) xyzz_madd(acc, p);
+  }
+  return acc;
+}
+
+using G1Affine = Affine<Fp>;
+using G2Affine = Affine<Fp2>;
+using G1XYZZ = XYZZ<Fp>;
+using G2XYZZ = XYZZ<Fp2>;
+
+}  // namespace b200

@@ -1,0 +1,373 @@
+// fp.cuh -- K1: BLS12-381 base field Fp and Fp2 = Fp[u]/(u^2+1) on 12 x 32-bit limbs.
+//
+// Replaces every blst_fp_* / blst_fp2 operation the reference reaches through blst
+// (call sites /root/reference/src/eip2537.c:287,301,316 and everything
+// under blst_p1_*/blst_p2_*/pairing).  Montgomery form, R = 2^384, values kept fully reduced
+// in [0, p) so equality tests (needed by the exact exceptional-case handling in ec.cuh) are
+// plain limb compares.
+//
+// Device path: CIOS Montgomery multiplication written as PTX mad.lo.cc/madc.hi.cc carry
+// chains over an even/odd column split (ptxas fuses each lo/hi pair into one
+// IMAD.WIDE.U32 with a predicate carry); add/sub are add.cc/sub.cc chains.
+// Host path (B200_HD functions compiled by g++ for tests/host_emul only): the same
+// algorithms in portable 64-bit C++.  The shipped library never runs the host path.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_D __device__ __forceinline__
+// out-of-line on the device: keeps code size (and ptxas time) bounded where a call's cost is
+// noise next to the >= 3 Fp multiplications inside
+#define B200_HD_NI __host__ __device__ __noinline__
+#else
+#define B200_HD inline
+#define B200_D inline
+#define B200_HD_NI inline
+#endif
+
+#include "constants.cuh"
+
+namespace b200 {
+
+struct alignas(16) Fp {
+  uint32_t v[12];
+};
+struct Fp2 {
+  Fp c0, c1;
+};
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+B200_HD Fp fp_zero() {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = 0;
+  return r;
+}
+B200_HD Fp fp_load_const(const uint32_t* c) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = c[i];
+  return r;
+}
+B200_HD Fp fp_one() { return fp_load_const(C_ONE()); }
+B200_HD bool is_zero(const Fp& a) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) acc |= a.v[i];
+  return acc == 0;
+}
+B200_HD bool eq(const Fp& a, const Fp& b) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) acc |= a.v[i] ^ b.v[i];
+  return acc == 0;
+}
+
+// r = a - p if a >= p else a        (a < 2p; `top` is an extra carry word of a)
+B200_HD Fp fp_reduce_once(const Fp& a, uint32_t top) {
+  const uint32_t* p = C_P();
+  Fp t;
+  uint32_t borrow;
+#if defined(__CUDA_ARCH__)
+  asm("sub.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(a.v[0]), "r"(p[0]));
+#pragma unroll
+  for (int i = 1; i < 12; i++) asm("subc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(a.v[i]), "r"(p[i]));
+  asm("subc.u32 %0, %1, 0;" : "=r"(borrow) : "r"(top));   // borrow = top - 0 - B  (0 or -1 when top = 0)
+  bool keep_a = (borrow >> 31) != 0;                        // went negative => a < p
+#else
+  uint64_t b = 0;
+  for (int i = 0; i < 12; i++) {
+    uint64_t d = (uint64_t)a.v[i] - p[i] - b;
+    t.v[i] = (uint32_t)d;
+    b = (d >> 32) & 1;
+  }
+  borrow = (uint32_t)b;
+  bool keep_a = (borrow != 0) && (top == 0);
+#endif
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = keep_a ? a.v[i] : t.v[i];
+  return r;
+}
+
+B200_HD Fp add(const Fp& a, const Fp& b) {
+  Fp t;
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+  for (int i = 1; i < 12; i++) asm("addc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+  // p < 2^381: a + b < 2^382 never carries out of 12 limbs
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 12; i++) {
+    uint64_t s = (uint64_t)a.v[i] + b.v[i] + c;
+    t.v[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+#endif
+  return fp_reduce_once(t, 0);
+}
+
+B200_HD Fp sub(const Fp& a, const Fp& b) {
+  const uint32_t* p = C_P();
+  Fp t;
+#if defined(__CUDA_ARCH__)
+  uint32_t mask;
+  asm("sub.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+  for (int i = 1; i < 12; i++) asm("subc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+  asm("subc.u32 %0, 0, 0;" : "=r"(mask));   // 0 or 0xffffffff
+  asm("add.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(t.v[0]), "r"(p[0] & mask));
+#pragma unroll
+  for (int i = 1; i < 12; i++) asm("addc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(t.v[i]), "r"(p[i] & mask));
+#else
+  uint64_t bw = 0;
+  for (int i = 0; i < 12; i++) {
+    uint64_t d = (uint64_t)a.v[i] - b.v[i] - bw;
+    t.v[i] = (uint32_t)d;
+    bw = (d >> 32) & 1;
+  }
+  if (bw) {
+    uint64_t c = 0;
+    for (int i = 0; i < 12; i++) {
+      uint64_t s = (uint64_t)t.v[i] + p[i] + c;
+      t.v[i] = (uint32_t)s;
+      c = s >> 32;
+    }
+  }
+#endif
+  return t;
+}
+B200_HD Fp neg(const Fp& a) { return sub(fp_zero(), a); }
+B200_HD Fp dbl(const Fp& a) { return add(a, a); }
+
+// ------------------------------------------------------------------------------------------
+// Montgomery multiplication  r = a*b/2^384 mod p
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE)
+// Column-split CIOS.  Products a[j]*bi are 64-bit; products with even j land on word pairs
+// (j, j+1) and chain without overlap, products with odd j likewise one word higher.  Two
+// accumulators (`e` aligned to even columns, `o` to odd columns) therefore take pure
+// lo/hi carry chains, which ptxas maps to IMAD.WIDE.U32 with predicate carries.  After the
+// reduction row the window slides one word, which swaps the roles of the two accumulators.
+namespace detail {
+// acc[0..12) = a[0,2,..,10] * b  (fresh accumulator: plain wide products, no carries)
+B200_D void mul_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(acc[j]) : "r"(a[j]), "r"(b));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(acc[j + 1]) : "r"(a[j]), "r"(b));
+  }
+}
+// acc[0..13) += a[0,2,..,10] * b  -- one carry chain, one asm statement
+B200_D void mad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %13, %19, %0;\n\t"
+      "madc.hi.cc.u32 %1, %13, %19, %1;\n\t"
+      "madc.lo.cc.u32 %2, %14, %19, %2;\n\t"
+      "madc.hi.cc.u32 %3, %14, %19, %3;\n\t"
+      "madc.lo.cc.u32 %4, %15, %19, %4;\n\t"
+      "madc.hi.cc.u32 %5, %15, %19, %5;\n\t"
+      "madc.lo.cc.u32 %6, %16, %19, %6;\n\t"
+      "madc.hi.cc.u32 %7, %16, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %17, %19, %8;\n\t"
+      "madc.hi.cc.u32 %9, %17, %19, %9;\n\t"
+      "madc.lo.cc.u32 %10, %18, %19, %10;\n\t"
+      "madc.hi.cc.u32 %11, %18, %19, %11;\n\t"
+      "addc.u32 %12, %12, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12])
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[8]), "r"(a[10]), "r"(b));
+}
+// acc[0..13) += {P0,P2,..,P10} * m   (modulus limbs as immediates)
+#define B200_MADP_ROW(acc, m, Q0, Q1, Q2, Q3, Q4, Q5)                                           \
+  asm("mad.lo.cc.u32 %0, %14, %13, %0;\n\t"                                                     \
+      "madc.hi.cc.u32 %1, %14, %13, %1;\n\t"                                                    \
+      "madc.lo.cc.u32 %2, %15, %13, %2;\n\t"                                                    \
+      "madc.hi.cc.u32 %3, %15, %13, %3;\n\t"                                                    \
+      "madc.lo.cc.u32 %4, %16, %13, %4;\n\t"                                                    \
+      "madc.hi.cc.u32 %5, %16, %13, %5;\n\t"                                                    \
+      "madc.lo.cc.u32 %6, %17, %13, %6;\n\t"                                                    \
+      "madc.hi.cc.u32 %7, %17, %13, %7;\n\t"                                                    \
+      "madc.lo.cc.u32 %8, %18, %13, %8;\n\t"                                                    \
+      "madc.hi.cc.u32 %9, %18, %13, %9;\n\t"                                                    \
+      "madc.lo.cc.u32 %10, %19, %13, %10;\n\t"                                                  \
+      "madc.hi.cc.u32 %11, %19, %13, %11;\n\t"                                                  \
+      "addc.u32 %12, %12, 0;"                                                                    \
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),      \
+        "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]),    \
+        "+r"(acc[12])                                                                            \
+      : "r"(m), "n"(Q0), "n"(Q1), "n"(Q2), "n"(Q3), "n"(Q4), "n"(Q5))
+// dst[0..12) += src[1..13), carry into dst[12]
+B200_D void fold(uint32_t* dst, const uint32_t* src) {
+  asm("add.cc.u32 %0, %0, %13;\n\t"
+      "addc.cc.u32 %1, %1, %14;\n\t"
+      "addc.cc.u32 %2, %2, %15;\n\t"
+      "addc.cc.u32 %3, %3, %16;\n\t"
+      "addc.cc.u32 %4, %4, %17;\n\t"
+      "addc.cc.u32 %5, %5, %18;\n\t"
+      "addc.cc.u32 %6, %6, %19;\n\t"
+      "addc.cc.u32 %7, %7, %20;\n\t"
+      "addc.cc.u32 %8, %8, %21;\n\t"
+      "addc.cc.u32 %9, %9, %22;\n\t"
+      "addc.cc.u32 %10, %10, %23;\n\t"
+      "addc.cc.u32 %11, %11, %24;\n\t"
+      "addc.u32 %12, %12, 0;"
+      : "+r"(dst[0]), "+r"(dst[1]), "+r"(dst[2]), "+r"(dst[3]), "+r"(dst[4]), "+r"(dst[5]), "+r"(dst[6]),
+        "+r"(dst[7]), "+r"(dst[8]), "+r"(dst[9]), "+r"(dst[10]), "+r"(dst[11]), "+r"(dst[12])
+      : "r"(src[1]), "r"(src[2]), "r"(src[3]), "r"(src[4]), "r"(src[5]), "r"(src[6]), "r"(src[7]),
+        "r"(src[8]), "r"(src[9]), "r"(src[10]), "r"(src[11]), "r"(src[12]));
+}
+}  // namespace detail
+
+B200_D Fp mul(const Fp& a, const Fp& b) {
+  using namespace detail;
+  // x: accumulator aligned to the current lowest column, 13 words; y: one column higher
+  uint32_t x[13], y[13];
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    uint32_t m;
+    // ---- row i: x is the low-aligned accumulator (fresh when i == 0), y is fresh
+    if (i == 0) { mul_row(x, a.v, b.v[0]); x[12] = 0; }
+    else        mad_row(x, a.v, b.v[i]);
+    mul_row(y, a.v + 1, b.v[i]); y[12] = 0;
+    m = x[0] * B200_M0;
+    B200_MADP_ROW(x, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+    B200_MADP_ROW(y, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+    fold(y, x);          // slide one column: y is now the low-aligned accumulator
+    // ---- row i+1: roles swapped
+    mad_row(y, a.v, b.v[i + 1]);
+    mul_row(x, a.v + 1, b.v[i + 1]); x[12] = 0;
+    m = y[0] * B200_M0;
+    B200_MADP_ROW(y, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+    B200_MADP_ROW(x, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+    fold(x, y);
+  }
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = x[i];
+  return fp_reduce_once(r, x[12]);
+}
+#else
+B200_HD Fp mul(const Fp& a, const Fp& b) {
+  const uint32_t* p = C_P();
+  uint32_t t[14];
+#pragma unroll
+  for (int i = 0; i < 14; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    uint64_t carry = 0, acc;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      acc = (uint64_t)a.v[j] * b.v[i] + t[j] + carry;
+      t[j] = (uint32_t)acc;
+      carry = acc >> 32;
+    }
+    acc = (uint64_t)t[12] + carry;
+    t[12] = (uint32_t)acc;
+    t[13] = (uint32_t)(acc >> 32);
+    uint32_t m = t[0] * B200_M0;
+    acc = (uint64_t)m * p[0] + t[0];
+    carry = acc >> 32;
+#pragma unroll
+    for (int j = 1; j < 12; j++) {
+      acc = (uint64_t)m * p[j] + t[j] + carry;
+      t[j - 1] = (uint32_t)acc;
+      carry = acc >> 32;
+    }
+    acc = (uint64_t)t[12] + carry;
+    t[11] = (uint32_t)acc;
+    t[12] = t[13] + (uint32_t)(acc >> 32);
+  }
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = t[i];
+  return fp_reduce_once(r, t[12]);
+}
+#endif
+B200_HD Fp sqr(const Fp& a) { return mul(a, a); }
+
+B200_HD Fp fp_to_mont(const Fp& a) { return mul(a, fp_load_const(C_RR())); }
+B200_HD Fp fp_from_mont(const Fp& a) {
+  Fp one = fp_zero();
+  one.v[0] = 1;
+  return mul(a, one);
+}
+
+// a^(p-2); inverse of 0 is 0 (same convention the reference relies on in blst_p1_to_affine)
+B200_HD_NI Fp inv(const Fp& a) {
+  const uint32_t* p = C_P();
+  // fixed 4-bit window over the public exponent p-2
+  Fp tbl[16];
+  tbl[0] = fp_one();
+  tbl[1] = a;
+  for (int i = 2; i < 16; i++) tbl[i] = mul(tbl[i - 1], a);
+  Fp acc = fp_one();
+  for (int w = 95; w >= 0; w--) {
+    uint32_t word = p[w >> 3];
+    if (w == 0) word -= 2;  // low nibble of p is 0xb, no borrow
+    uint32_t d = (word >> (4 * (w & 7))) & 0xF;
+    if (w != 95) {
+      acc = sqr(acc); acc = sqr(acc); acc = sqr(acc); acc = sqr(acc);
+    }
+    if (d) acc = mul(acc, tbl[d]);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fp2
+// ------------------------------------------------------------------------------------------
+B200_HD Fp2 fp2_zero() { Fp2 r; r.c0 = fp_zero(); r.c1 = fp_zero(); return r; }
+B200_HD Fp2 fp2_one() { Fp2 r; r.c0 = fp_one(); r.c1 = fp_zero(); return r; }
+B200_HD Fp2 fp2_load_const(const uint32_t* c) { Fp2 r; r.c0 = fp_load_const(c); r.c1 = fp_load_const(c + 12); return r; }
+B200_HD bool is_zero(const Fp2& a) { return is_zero(a.c0) && is_zero(a.c1); }
+B200_HD bool eq(const Fp2& a, const Fp2& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c1); }
+B200_HD Fp2 add(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = add(a.c0, b.c0); r.c1 = add(a.c1, b.c1); return r; }
+B200_HD Fp2 sub(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = sub(a.c0, b.c0); r.c1 = sub(a.c1, b.c1); return r; }
+B200_HD Fp2 neg(const Fp2& a) { Fp2 r; r.c0 = neg(a.c0); r.c1 = neg(a.c1); return r; }
+B200_HD Fp2 dbl(const Fp2& a) { return add(a, a); }
+B200_HD Fp2 conj(const Fp2& a) { Fp2 r; r.c0 = a.c0; r.c1 = neg(a.c1); return r; }
+B200_HD_NI Fp2 mul(const Fp2& a, const Fp2& b) {
+  Fp t0 = mul(a.c0, b.c0), t1 = mul(a.c1, b.c1);
+  Fp t2 = mul(add(a.c0, a.c1), add(b.c0, b.c1));
+  Fp2 r;
+  r.c0 = sub(t0, t1);
+  r.c1 = sub(sub(t2, t0), t1);
+  return r;
+}
+B200_HD_NI Fp2 sqr(const Fp2& a) {
+  Fp2 r;
+  Fp m = mul(a.c0, a.c1);
+  r.c0 = mul(add(a.c0, a.c1), sub(a.c0, a.c1));
+  r.c1 = dbl(m);
+  return r;
+}
+B200_HD_NI Fp2 mul_fp(const Fp2& a, const Fp& k) { Fp2 r; r.c0 = mul(a.c0, k); r.c1 = mul(a.c1, k); return r; }
+B200_HD Fp2 mul_xi(const Fp2& a) { Fp2 r; r.c0 = sub(a.c0, a.c1); r.c1 = add(a.c0, a.c1); return r; }
+B200_HD Fp2 inv(const Fp2& a) {
+  Fp t = inv(add(sqr(a.c0), sqr(a.c1)));
+  Fp2 r;
+  r.c0 = mul(a.c0, t);
+  r.c1 = neg(mul(a.c1, t));
+  return r;
+}
+
+// field "traits" used by the field-generic point code
+template <class F> struct FieldOps;
+template <> struct FieldOps<Fp> {
+  static B200_HD Fp zero() { return fp_zero(); }
+  static B200_HD Fp one() { return fp_one(); }
+  static B200_HD Fp curve_b() { return fp_load_const(C_B1()); }
+  static constexpr int WORDS = 12;
+};
+template <> struct FieldOps<Fp2> {
+  static B200_HD Fp2 zero() { return fp2_zero(); }
+  static B200_HD Fp2 one() { return fp2_one(); }
+  static B200_HD Fp2 curve_b() { return fp2_load_const(C_B2()); }
+  static constexpr int WORDS = 24;
+};
+
+}  // namespace b200

@@ -1,0 +1,283 @@
+// msm.cuh -- K3 (batched decode) + K4 (Pippenger bucket MSM) kernels, field-generic (G1: Fp, G2: Fp2).
+//
+// Replaces the reference's MULTIEXP strategies -- k=1 blst_p*_mult, k<=4 naive per-pair
+// scalar multiplications, k>4 Bos-Coster heap (/root/reference/src/eip2537.c:541-708 for G1,
+// :829-998 for G2) -- with one data-parallel pipeline:
+//
+//   decode      one thread per pair: wire bytes -> Montgomery affine point + status; the first
+//               failing pair (minimum index) decides the error code, as the reference's
+//               sequential loops do (:580-592, :650-668)
+//   digits      one thread per scalar: full 256-bit scalar (never reduced mod r, :417-420)
+//               -> signed c-bit digits (top window unsigned, so no 257th-bit window) +
+//               per-bucket histogram
+//   scan        exclusive prefix sum of the histogram (bucket segment offsets)
+//   scatter     counting-sort the (bucket <- point index | sign) entries into segments
+//   accumulate  one thread per bucket: XYZZ += affine point (mixed add, exact exceptional cases)
+//   reduce      sum_b b*B_b per window by a tree of (plain sum, weighted sum) nodes
+//   final       Horner over windows, to-affine (one inversion), encode to wire bytes
+//
+// Result = encode(affine(sum k_i * P_i)) in the FULL curve group: no GLV, no mod-r reduction,
+// because MULTIEXP inputs are not subgroup-checked.
+#pragma once
+#include "codec.cuh"
+
+namespace b200 {
+
+struct MsmPlan {
+  int c;          // window width in bits (2..16)
+  int nwin;       // ceil(256 / c)
+  int top_bits;   // bits in the top window = 256 - c*(nwin-1)
+  int log_nb;     // log2(buckets per window) = max(c-1, top_bits)
+  uint32_t nb;    // buckets per window (uniform layout), power of two
+};
+
+static inline MsmPlan make_plan(int c) {
+  MsmPlan p;
+  p.c = c;
+  p.nwin = (256 + c - 1) / c;
+  p.top_bits = 256 - c * (p.nwin - 1);
+  p.log_nb = (c - 1 > p.top_bits) ? c - 1 : p.top_bits;
+  p.nb = 1u << p.log_nb;
+  return p;
+}
+
+#ifdef __CUDACC__
+
+static constexpr unsigned long long STATUS_OK = ~0ull;
+
+// ------------------------------------------------------------------------------------------ decode
+// status key = (pair index << 8) | code ; atomicMin keeps the first failing pair
+template <class F>
+__global__ void __launch_bounds__(128) k_decode(const uint32_t* __restrict__ raw, size_t n, Affine<F>* __restrict__ pts,
+                                                unsigned long long* status, size_t index_base) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int PW = Wire<F>::POINT_WORDS, SW = Wire<F>::PAIR_WORDS;
+  uint32_t w[PW];
+  const uint4* src = reinterpret_cast<const uint4*>(raw + i * SW);
+#pragma unroll
+  for (int k = 0; k < PW / 4; k++) {
+    uint4 q = __ldg(src + k);
+    w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+  }
+  Affine<F> pt;
+  int code = decode_point(pt, w);
+  if (code != E_SUCCESS) atomicMin(status, ((unsigned long long)(index_base + i) << 8) | (unsigned)code);
+  pts[i] = pt;
+}
+
+// ------------------------------------------------------------------------------------------ digits
+__device__ __forceinline__ uint32_t window_bits(const uint32_t* k, int bit, int c) {
+  int word = bit >> 5, sh = bit & 31;
+  uint32_t v = k[word] >> sh;
+  if (sh + c > 32 && word + 1 < 8) v |= k[word + 1] << (32 - sh);
+  return v & ((1u << c) - 1);
+}
+
+// digits[w*n + i] = signed digit of scalar i in window w (0 = skip); counts[w*nb + |d|-1]++
+template <class F>
+__global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ raw, size_t n, const Affine<F>* __restrict__ pts,
+                                                MsmPlan plan, int* __restrict__ digits, uint32_t* counts) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int PW = Wire<F>::POINT_WORDS, SW = Wire<F>::PAIR_WORDS;
+  const uint4* src = reinterpret_cast<const uint4*>(raw + i * SW + PW);
+  uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
+  uint32_t sw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w}, k[8];
+  scalar_from_slot(k, sw);
+  // a point at infinity contributes nothing whatever its scalar
+  const uint32_t* pw = reinterpret_cast<const uint32_t*>(pts + i);
+  uint32_t any = 0;
+  for (int t = 0; t < (int)(sizeof(Affine<F>) / 4); t++) any |= pw[t];
+  bool inf = (any == 0);
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (plan.c - 1);
+  for (int w = 0; w < plan.nwin; w++) {
+    int d;
+    if (w < plan.nwin - 1) {
+      uint32_t raw_d = window_bits(k, w * plan.c, plan.c) + carry;
+      if (raw_d > half) { d = (int)raw_d - (int)(1u << plan.c); carry = 1; }
+      else              { d = (int)raw_d; carry = 0; }
+    } else {
+      d = (int)(window_bits(k, w * plan.c, plan.top_bits) + carry);   // top window: unsigned, <= 2^top_bits
+    }
+    if (inf) d = 0;
+    digits[(size_t)w * n + i] = d;
+    if (d != 0) {
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      atomicAdd(&counts[(size_t)w * plan.nb + (mag - 1)], 1u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ scan
+// three-kernel exclusive scan over m counters (m <= ~2^21): block-local scan, scan of block sums, fix-up
+__global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                      uint32_t* __restrict__ block_sums, uint32_t m) {
+  __shared__ uint32_t warp_sums[32];
+  uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+  uint32_t v = i < m ? in[i] : 0, x = v;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = warp_sums[lane], t = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+    warp_sums[lane] = t - s;
+    if (lane == 31) block_sums[blockIdx.x] = t;
+  }
+  __syncthreads();
+  if (i < m) out[i] = x - v + warp_sums[wid];
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* block_sums, uint32_t nblocks) {
+  // single block, sequential over tiles of 1024
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < nblocks; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < nblocks ? block_sums[i] : 0, x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t s = warp_sums[lane], t = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+      warp_sums[lane] = t - s;
+    }
+    __syncthreads();
+    uint32_t excl = x - v + warp_sums[wid] + carry_s;
+    if (i < nblocks) block_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(1024) k_scan_fix(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_sums, uint32_t m) {
+  uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+  if (i < m) out[i] += block_sums[blockIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------ scatter
+// entries[offsets[b] + k] = point index | sign<<31 ; order inside a bucket is irrelevant
+// (the group is commutative and the affine result is unique)
+__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits, size_t n, MsmPlan plan,
+                                                 const uint32_t* __restrict__ offsets, uint32_t* cursors,
+                                                 uint32_t* __restrict__ entries) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (size_t)plan.nwin) return;
+  size_t w = t / n, i = t - w * n;
+  int d = digits[t];
+  if (d == 0) return;
+  uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+  size_t b = w * plan.nb + (mag - 1);
+  uint32_t pos = atomicAdd(&cursors[b], 1u);
+  entries[offsets[b] + pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------ accumulate
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
+  Affine<F> r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(Affine<F>) / 16); k++) d[k] = __ldg(s + k);
+  return r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                    const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                    uint32_t nbuckets_total, XYZZ<F>* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets_total) return;
+  uint32_t start = offsets[b], cnt = counts[b];
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (uint32_t k = 0; k < cnt; k++) {
+    uint32_t e = __ldg(entries + start + k);
+    Affine<F> pt = load_affine(pts + (e & 0x7fffffffu));
+    if (e >> 31) pt.y = neg(pt.y);
+    xyzz_madd(acc, pt);
+  }
+  buckets[b] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ reduce
+// A node covers a power-of-two range of consecutive buckets of one window and carries
+//   s = sum of its buckets,  w = sum over its buckets of (1-based offset inside the node) * bucket
+template <class F>
+struct Node { XYZZ<F> s, w; };
+
+// level 0: each thread folds `L` consecutive buckets (bucket magnitudes lo+1 .. lo+L) by a running sum
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_leaf(const XYZZ<F>* __restrict__ buckets, uint32_t nnodes_total, int L,
+                                                     Node<F>* __restrict__ nodes) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnodes_total) return;
+  const XYZZ<F>* b = buckets + (size_t)t * L;
+  XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>();
+  for (int j = L - 1; j >= 0; j--) {
+    XYZZ<F> v = b[j];
+    xyzz_add(run, v);
+    xyzz_add(acc, run);
+  }
+  nodes[t].s = run;
+  nodes[t].w = acc;
+}
+// inner level: fold L children, each covering 2^log_m buckets:
+//   s = sum s_t ;  w = sum w_t + 2^log_m * sum_t t*s_t   (t = 0..L-1)
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_inner(const Node<F>* __restrict__ in, uint32_t nout_total, int L, int log_m,
+                                                      Node<F>* __restrict__ out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nout_total) return;
+  const Node<F>* ch = in + (size_t)t * L;
+  XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>(), wsum = xyzz_inf<F>();
+  for (int j = L - 1; j >= 0; j--) {
+    XYZZ<F> cw = ch[j].w;
+    xyzz_add(wsum, cw);
+    xyzz_add(acc, run);
+    XYZZ<F> cs = ch[j].s;
+    xyzz_add(run, cs);
+  }
+  for (int k = 0; k < log_m; k++) acc = xyzz_dbl(acc);
+  xyzz_add(wsum, acc);
+  out[t].s = run;
+  out[t].w = wsum;
+}
+
+// window totals T_w = roots[w].w ; result = sum_w 2^(c*w) T_w  (Horner from the top window)
+template <class F>
+__global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan, XYZZ<F>* __restrict__ out_partial) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<F> acc = roots[plan.nwin - 1].w;
+  for (int w = plan.nwin - 2; w >= 0; w--) {
+    for (int k = 0; k < plan.c; k++) acc = xyzz_dbl(acc);
+    XYZZ<F> t = roots[w].w;
+    xyzz_add(acc, t);
+  }
+  *out_partial = acc;
+}
+
+// sum `count` partial results (multi-GPU gather, or count = 1), convert to affine, encode
+template <class F>
+__global__ void k_finalize(const XYZZ<F>* __restrict__ partials, int count, uint32_t* __restrict__ out_words) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<F> acc = partials[0];
+  for (int i = 1; i < count; i++) { XYZZ<F> t = partials[i]; xyzz_add(acc, t); }
+  Affine<F> a = xyzz_to_affine(acc);
+  uint32_t w[Wire<F>::POINT_WORDS];
+  encode_point(w, a);
+  for (int i = 0; i < Wire<F>::POINT_WORDS; i++) out_words[i] = w[i];
+}
+
+#endif  // __CUDACC__
+}  // namespace b200

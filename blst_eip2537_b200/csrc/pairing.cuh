@@ -1,0 +1,311 @@
+// pairing.cuh -- K5: batched optimal-ate pairing checks over BLS12-381 (+ K3 subgroup checks).
+//
+// Replaces, for many independent calls at once, the body of bls12_pairing
+// (/root/reference/src/eip2537.c:1020-1081): per pair decode_g1_point (:1036),
+// blst_p1_affine_in_g1 (:1041), decode_g2_point (:1046), blst_p2_affine_in_g2 (:1051),
+// blst_miller_loop (:1060/:1065), blst_fp12_mul (:1061); per call blst_final_exp (:1070) and
+// blst_fp12_is_one (:1076).  Only the boolean leaves the function, so the Miller-loop
+// variant and the final-exponent multiple (here 3*(p^12-1)/r) are free choices
+// (SURVEY.md Appendix D-8); a pair with an infinite member contributes 1 (Appendix D-2).
+//
+// Tower: Fp2 = Fp[u]/(u^2+1), Fp6 = Fp2[v]/(v^3 - (1+u)), Fp12 = Fp6[w]/(w^2 - v).
+// Lines are sparse elements l0 + l1*w^2 + l4*w^3 ("014").
+#pragma once
+#include "codec.cuh"
+
+namespace b200 {
+
+struct Fp6 { Fp2 c0, c1, c2; };
+struct Fp12 { Fp6 c0, c1; };
+
+// out-of-line Fp2 kernels keep the (very large) pairing code compact
+// Fp2 mul / sqr / mul_fp and Fp inv are out-of-line on the device (fp.cuh), which keeps the
+// (very large) pairing code compact
+B200_HD Fp2 mulo(const Fp2& a, const Fp2& b) { return mul(a, b); }
+B200_HD Fp2 sqro(const Fp2& a) { return sqr(a); }
+B200_HD Fp2 mulfpo(const Fp2& a, const Fp& k) { return mul_fp(a, k); }
+B200_HD Fp2 fp2_inv_o(const Fp2& a) { return inv(a); }
+
+// ---------------------------------------------------------------- Fp6
+B200_HD void fp6_add(Fp6& r, const Fp6& a, const Fp6& b) { r.c0 = add(a.c0, b.c0); r.c1 = add(a.c1, b.c1); r.c2 = add(a.c2, b.c2); }
+B200_HD void fp6_sub(Fp6& r, const Fp6& a, const Fp6& b) { r.c0 = sub(a.c0, b.c0); r.c1 = sub(a.c1, b.c1); r.c2 = sub(a.c2, b.c2); }
+B200_HD void fp6_neg(Fp6& r, const Fp6& a) { r.c0 = neg(a.c0); r.c1 = neg(a.c1); r.c2 = neg(a.c2); }
+B200_HD void fp6_mul_v(Fp6& r, const Fp6& a) {
+  Fp2 t = mul_xi(a.c2);
+  r.c2 = a.c1; r.c1 = a.c0; r.c0 = t;
+}
+B200_HD_NI void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
+  Fp2 t0 = mulo(a.c0, b.c0), t1 = mulo(a.c1, b.c1), t2 = mulo(a.c2, b.c2);
+  Fp2 c0 = add(mul_xi(sub(sub(mulo(add(a.c1, a.c2), add(b.c1, b.c2)), t1), t2)), t0);
+  Fp2 c1 = add(sub(sub(mulo(add(a.c0, a.c1), add(b.c0, b.c1)), t0), t1), mul_xi(t2));
+  Fp2 c2 = add(sub(sub(mulo(add(a.c0, a.c2), add(b.c0, b.c2)), t0), t2), t1);
+  r.c0 = c0; r.c1 = c1; r.c2 = c2;
+}
+// a * (b0 + b1 v)
+B200_HD_NI void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
+  Fp2 aa = mulo(a.c0, b0), bb = mulo(a.c1, b1);
+  Fp2 c0 = add(mul_xi(sub(mulo(add(a.c1, a.c2), b1), bb)), aa);
+  Fp2 c1 = sub(sub(mulo(add(b0, b1), add(a.c0, a.c1)), aa), bb);
+  Fp2 c2 = add(sub(mulo(add(a.c0, a.c2), b0), aa), bb);
+  r.c0 = c0; r.c1 = c1; r.c2 = c2;
+}
+// a * (b1 v)
+B200_HD_NI void fp6_mul_by_1(Fp6& r, const Fp6& a, const Fp2& b1) {
+  Fp2 c0 = mul_xi(mulo(a.c2, b1)), c1 = mulo(a.c0, b1), c2 = mulo(a.c1, b1);
+  r.c0 = c0; r.c1 = c1; r.c2 = c2;
+}
+B200_HD_NI void fp6_inv(Fp6& r, const Fp6& a) {
+  Fp2 t0 = sub(sqro(a.c0), mul_xi(mulo(a.c1, a.c2)));
+  Fp2 t1 = sub(mul_xi(sqro(a.c2)), mulo(a.c0, a.c1));
+  Fp2 t2 = sub(sqro(a.c1), mulo(a.c0, a.c2));
+  Fp2 d = add(mul_xi(add(mulo(a.c2, t1), mulo(a.c1, t2))), mulo(a.c0, t0));
+  d = fp2_inv_o(d);
+  r.c0 = mulo(t0, d); r.c1 = mulo(t1, d); r.c2 = mulo(t2, d);
+}
+
+// ---------------------------------------------------------------- Fp12
+B200_HD void fp12_set_one(Fp12& r) {
+  r.c0.c0 = fp2_one(); r.c0.c1 = fp2_zero(); r.c0.c2 = fp2_zero();
+  r.c1.c0 = fp2_zero(); r.c1.c1 = fp2_zero(); r.c1.c2 = fp2_zero();
+}
+B200_HD bool fp12_is_one(const Fp12& a) {
+  return eq(a.c0.c0, fp2_one()) && is_zero(a.c0.c1) && is_zero(a.c0.c2) && is_zero(a.c1.c0) && is_zero(a.c1.c1) && is_zero(a.c1.c2);
+}
+B200_HD_NI void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
+  Fp6 t0, t1, s, u, c1;
+  fp6_mul(t0, a.c0, b.c0);
+  fp6_mul(t1, a.c1, b.c1);
+  fp6_add(s, a.c0, a.c1); fp6_add(u, b.c0, b.c1);
+  fp6_mul(c1, s, u);
+  fp6_sub(c1, c1, t0); fp6_sub(c1, c1, t1);
+  fp6_mul_v(t1, t1);
+  fp6_add(r.c0, t0, t1);
+  r.c1 = c1;
+}
+B200_HD_NI void fp12_sqr(Fp12& r, const Fp12& a) {
+  Fp6 ab, s, t, vab;
+  fp6_mul(ab, a.c0, a.c1);
+  fp6_add(s, a.c0, a.c1);
+  fp6_mul_v(t, a.c1); fp6_add(t, t, a.c0);
+  fp6_mul(s, s, t);
+  fp6_mul_v(vab, ab);
+  fp6_sub(s, s, ab); fp6_sub(r.c0, s, vab);
+  fp6_add(r.c1, ab, ab);
+}
+B200_HD void fp12_conj(Fp12& r, const Fp12& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
+B200_HD_NI void fp12_inv(Fp12& r, const Fp12& a) {
+  Fp6 t0, t1;
+  fp6_mul(t0, a.c0, a.c0); fp6_mul(t1, a.c1, a.c1); fp6_mul_v(t1, t1); fp6_sub(t0, t0, t1);
+  fp6_inv(t0, t0);
+  fp6_mul(r.c0, a.c0, t0);
+  fp6_mul(t1, a.c1, t0); fp6_neg(r.c1, t1);
+}
+// f *= l0 + l1 w^2 + l4 w^3   (13 Fp2 products)
+B200_HD_NI void fp12_mul_by_014(Fp12& f, const Fp2& l0, const Fp2& l1, const Fp2& l4) {
+  Fp6 aa, bb, s, c1;
+  fp6_mul_by_01(aa, f.c0, l0, l1);
+  fp6_mul_by_1(bb, f.c1, l4);
+  Fp2 o = add(l1, l4);
+  fp6_add(s, f.c0, f.c1);
+  fp6_mul_by_01(c1, s, l0, o);
+  fp6_sub(c1, c1, aa); fp6_sub(c1, c1, bb);
+  fp6_mul_v(bb, bb);
+  fp6_add(f.c0, aa, bb);
+  f.c1 = c1;
+}
+B200_HD Fp2& fp12_wcoef(Fp12& a, int i) {   // coefficient of w^i
+  Fp6& h = (i & 1) ? a.c1 : a.c0;
+  return (i >> 1) == 0 ? h.c0 : ((i >> 1) == 1 ? h.c1 : h.c2);
+}
+B200_HD_NI void fp12_frob(Fp12& r, const Fp12& a, int k) {   // k = 1 or 2
+  Fp12 t = a;
+  const uint32_t* tab = (k == 1) ? C_FROB1() : C_FROB2();
+  for (int i = 0; i < 6; i++) {
+    Fp2& c = fp12_wcoef(t, i);
+    if (k == 1) c = conj(c);
+    c = mulo(c, fp2_load_const(tab + 24 * i));
+  }
+  r = t;
+}
+// Granger-Scott squaring in the cyclotomic subgroup
+B200_HD void fp4_sqr(Fp2& r0, Fp2& r1, const Fp2& a, const Fp2& b) {
+  Fp2 t0 = sqro(a), t1 = sqro(b);
+  r1 = sub(sub(sqro(add(a, b)), t0), t1);
+  r0 = add(mul_xi(t1), t0);
+}
+B200_HD_NI void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
+  Fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+  Fp2 t0, t1, t2, t3, u0, u1;
+  fp4_sqr(t0, t1, z0, z1);
+  z0 = add(dbl(sub(t0, z0)), t0);
+  z1 = add(dbl(add(t1, z1)), t1);
+  fp4_sqr(u0, u1, z2, z3);
+  fp4_sqr(t2, t3, z4, z5);
+  z4 = add(dbl(sub(u0, z4)), u0);
+  z5 = add(dbl(add(u1, z5)), u1);
+  t0 = mul_xi(t3);
+  z2 = add(dbl(add(t0, z2)), t0);
+  z3 = add(dbl(sub(t2, z3)), t2);
+  r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
+  r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
+}
+
+// ---------------------------------------------------------------- Miller loop
+struct G2Proj { Fp2 x, y, z; };   // homogeneous projective point on the twist
+
+B200_HD_NI void ml_dbl_step(G2Proj& t, Fp2& l0, Fp2& l1, Fp2& l4) {
+  const Fp inv2 = fp_load_const(C_INV2());
+  Fp2 a = mulfpo(mulo(t.x, t.y), inv2);
+  Fp2 b = sqro(t.y), c = sqro(t.z);
+  Fp2 e = mulo(fp2_load_const(C_B2X3()), c);
+  Fp2 f = add(dbl(e), e);
+  Fp2 g = mulfpo(add(b, f), inv2);
+  Fp2 h = sub(sqro(add(t.y, t.z)), add(b, c));
+  Fp2 j = sqro(t.x);
+  Fp2 e2 = sqro(e);
+  l0 = sub(e, b);
+  t.x = mulo(a, sub(b, f));
+  t.y = sub(sqro(g), add(dbl(e2), e2));
+  t.z = mulo(b, h);
+  l1 = add(dbl(j), j);
+  l4 = neg(h);
+}
+B200_HD_NI void ml_add_step(G2Proj& t, const G2Affine& q, Fp2& l0, Fp2& l1, Fp2& l4) {
+  Fp2 theta = sub(t.y, mulo(q.y, t.z));
+  Fp2 lam = sub(t.x, mulo(q.x, t.z));
+  Fp2 c = sqro(theta), d = sqro(lam);
+  Fp2 e = mulo(lam, d), f = mulo(t.z, c), g = mulo(t.x, d);
+  Fp2 h = sub(add(e, f), dbl(g));
+  t.x = mulo(lam, h);
+  t.y = sub(mulo(theta, sub(g, h)), mulo(e, t.y));
+  t.z = mulo(t.z, e);
+  l0 = sub(mulo(theta, q.x), mulo(lam, q.y));
+  l1 = neg(theta);
+  l4 = lam;
+}
+// f = conj( f_{|z|,Q}(P) ) ; infinity on either side -> 1
+B200_HD_NI void miller_loop(Fp12& f, const G1Affine& p, const G2Affine& q) {
+  fp12_set_one(f);
+  if (is_inf(p) || is_inf(q)) return;
+  G2Proj t;
+  t.x = q.x; t.y = q.y; t.z = fp2_one();
+  Fp2 l0, l1, l4;
+  for (int i = 62; i >= 0; i--) {
+    if (i != 62) fp12_sqr(f, f);
+    ml_dbl_step(t, l0, l1, l4);
+    fp12_mul_by_014(f, l0, mulfpo(l1, p.x), mulfpo(l4, p.y));
+    if ((B200_Z_ABS >> i) & 1) {
+      ml_add_step(t, q, l0, l1, l4);
+      fp12_mul_by_014(f, l0, mulfpo(l1, p.x), mulfpo(l4, p.y));
+    }
+  }
+  fp12_conj(f, f);
+}
+
+// ---------------------------------------------------------------- final exponentiation
+B200_HD_NI void cyc_exp_z(Fp12& r, const Fp12& a) {   // a^z, z < 0, a in the cyclotomic subgroup
+  Fp12 acc = a;
+  for (int i = 62; i >= 0; i--) {
+    fp12_cyclotomic_sqr(acc, acc);
+    if ((B200_Z_ABS >> i) & 1) fp12_mul(acc, acc, a);
+  }
+  fp12_conj(r, acc);
+}
+// f^((p^6-1)(p^2+1)) then ^((z-1)^2 (z+p)(z^2+p^2-1)) * ^3  =  f^(3 (p^12-1)/r)
+B200_HD_NI void final_exp(Fp12& r, const Fp12& fin) {
+  Fp12 f, t0, t1, t2, u;
+  fp12_inv(t0, fin); fp12_conj(f, fin); fp12_mul(f, f, t0);
+  fp12_frob(t0, f, 2); fp12_mul(f, t0, f);
+  cyc_exp_z(t0, f); fp12_conj(u, f); fp12_mul(t0, t0, u);
+  cyc_exp_z(t1, t0); fp12_conj(u, t0); fp12_mul(t0, t1, u);
+  cyc_exp_z(t1, t0); fp12_frob(u, t0, 1); fp12_mul(t1, t1, u);
+  cyc_exp_z(t2, t1); cyc_exp_z(u, t2);
+  fp12_frob(t2, t1, 2); fp12_mul(t2, u, t2);
+  fp12_conj(u, t1); fp12_mul(t2, t2, u);
+  fp12_cyclotomic_sqr(u, f); fp12_mul(u, u, f);
+  fp12_mul(r, t2, u);
+}
+
+// ---------------------------------------------------------------- subgroup membership (Scott 2021)
+// G1: phi(P) = (beta x, y) == [-z^2]P ;  G2: psi(Q) == [z]Q.  Infinity is a member.
+B200_HD_NI bool g1_in_subgroup(const G1Affine& p) {
+  if (is_inf(p)) return true;
+  const uint32_t zsq[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};   // z^2, little-endian words
+  G1XYZZ q = xyzz_scalar_mul(p, zsq, 128);
+  if (is_inf(q)) return false;
+  // compare phi(P) with -q without leaving XYZZ: beta*x*ZZ == X and  y*ZZZ == -Y
+  Fp bx = mul(p.x, fp_load_const(C_BETA()));
+  return eq(mul(bx, q.zz), q.x) && eq(mul(p.y, q.zzz), neg(q.y));
+}
+B200_HD_NI bool g2_in_subgroup(const G2Affine& p) {
+  if (is_inf(p)) return true;
+  const uint32_t zabs[2] = {(uint32_t)(B200_Z_ABS & 0xffffffffu), (uint32_t)(B200_Z_ABS >> 32)};
+  G2XYZZ q = xyzz_scalar_mul(p, zabs, 64);
+  if (is_inf(q)) return false;
+  Fp2 px = mulo(conj(p.x), fp2_load_const(C_PSI_CX()));
+  Fp2 py = mulo(conj(p.y), fp2_load_const(C_PSI_CY()));
+  return eq(mulo(px, q.zz), q.x) && eq(mulo(py, q.zzz), neg(q.y));   // [z]Q = -[|z|]Q
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- kernels
+// pair_call[j] = index of the call that owns pair j   (offsets are byte offsets, 384 B per pair)
+__global__ void k_pairing_index(const unsigned long long* __restrict__ offsets, size_t n_calls, uint32_t* __restrict__ pair_call) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_calls) return;
+  size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
+  for (size_t j = first; j < last; j++) pair_call[j] = (uint32_t)i;
+}
+
+// one thread per pair: decode + subgroup checks in the reference's order
+// (G1 decode, G1 subgroup, G2 decode, G2 subgroup; eip2537.c:1036-1053); status[j] = first failing code
+__global__ void __launch_bounds__(64) k_pairing_decode(const uint32_t* __restrict__ raw, size_t total_pairs,
+                                                       G1Affine* __restrict__ g1, G2Affine* __restrict__ g2, int* __restrict__ status) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total_pairs) return;
+  const uint4* src = reinterpret_cast<const uint4*>(raw + j * 96);
+  uint32_t w[64];
+  int code;
+  G1Affine p;
+  G2Affine q;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { uint4 v = __ldg(src + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+  code = decode_point(p, w);
+  if (code == E_SUCCESS && !g1_in_subgroup(p)) code = E_NOT_IN_SUBGROUP;
+  if (code == E_SUCCESS) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) { uint4 v = __ldg(src + 8 + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+    code = decode_point(q, w);
+    if (code == E_SUCCESS && !g2_in_subgroup(q)) code = E_NOT_IN_SUBGROUP;
+  }
+  status[j] = code;
+  if (code == E_SUCCESS) { g1[j] = p; g2[j] = q; }
+}
+
+// one thread per call: first failing pair decides the error; otherwise product of the
+// pairs' Miller loops, one final exponentiation, is-one -> out[31]
+__global__ void __launch_bounds__(64) k_pairing_calls(const unsigned long long* __restrict__ offsets, size_t n_calls,
+                                                      const G1Affine* __restrict__ g1, const G2Affine* __restrict__ g2,
+                                                      const int* __restrict__ status, uint32_t* __restrict__ outs, int* __restrict__ errs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_calls) return;
+  size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
+  uint32_t* out = outs + 8 * i;
+  for (int k = 0; k < 8; k++) out[k] = 0;
+  if (first == last) { errs[i] = E_INVALID_LENGTH; return; }
+  for (size_t j = first; j < last; j++)
+    if (status[j] != E_SUCCESS) { errs[i] = status[j]; return; }
+  Fp12 acc, cur;
+  for (size_t j = first; j < last; j++) {
+    G1Affine p = g1[j];
+    G2Affine q = g2[j];
+    if (j == first) miller_loop(acc, p, q);
+    else { miller_loop(cur, p, q); fp12_mul(acc, acc, cur); }
+  }
+  final_exp(acc, acc);
+  if (fp12_is_one(acc)) out[7] = 0x01000000u;   // byte 31 of the 32-byte big-endian word
+  errs[i] = E_SUCCESS;
+}
+#endif  // __CUDACC__
+
+}  // namespace b200

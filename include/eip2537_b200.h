@@ -1,0 +1,71 @@
+/*
+ * eip2537_b200.h -- ADDITIVE extensions to the reference ABI (nothing in the reference calls
+ * these; SURVEY.md 8(b) "New (additive) exports for the batch configs").
+ *
+ * The legacy ABI (eip2537.h) is one call = one result with host buffers.  The data-parallel
+ * configurations of BASELINE.json need (1) many independent calls in one submission,
+ * (2) device-resident inputs for kernel-only timing and for multi-GPU sharding where each
+ * rank holds a slice in HBM, and (3) explicit lifetime control.  Semantics per call are
+ * identical to the single-call function of eip2537.h (same bytes, same codes).
+ *
+ * All pointers named d_* are CUDA device pointers, 16-byte aligned, on the current device.
+ * `stream` is a cudaStream_t passed as void* (NULL = the engine's own stream).
+ * Every function returns an EIP2537_ERROR; CUDA failures map to EIP2537_MEMORY_ERROR.
+ */
+#ifndef __EIP2537_B200_H__
+#define __EIP2537_B200_H__
+
+#include "eip2537.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* lifetime: lazy init happens on first use; these make it explicit.  device < 0 = current. */
+EIP2537_ERROR bls12_b200_init(int device);
+void bls12_b200_shutdown(void);
+/* last CUDA error string seen by the engine on this thread ("" if none) */
+const char* bls12_b200_last_error(void);
+/* number of kernels the engine has launched since process start (bench.py's gpu_launches) */
+uint64_t bls12_b200_launch_count(void);
+/* force the Pippenger window width (2..16); 0 = automatic */
+void bls12_b200_set_window(int c);
+
+/* ---- batch of independent calls, host buffers (replaces n calls of bls12_pairing /
+ *      bls12_g{1,2}multiexp; offsets[n+1] are byte offsets of each call's input in `in`).
+ *      outs = n*32 / n*128 / n*256 bytes; errs[n] per-call codes; outs of failed calls are zeroed. */
+EIP2537_ERROR bls12_pairing_batch(byte* outs, EIP2537_ERROR* errs, const byte* in,
+                                  const uint64_t* offsets, size_t n);
+
+/* ---- device-resident MSM (group = 1 for G1, 2 for G2).
+ *  d_in: n pairs in wire format (160*n / 288*n bytes).  d_out: 128 / 256 encoded bytes.
+ *  d_status: one uint64; ~0 on success else (first failing pair index << 8) | code.
+ *  Asynchronous on `stream`; the caller synchronises and reads d_status / d_out. */
+EIP2537_ERROR bls12_b200_msm_device(int group, const void* d_in, size_t n, void* d_out,
+                                    uint64_t* d_status, void* stream);
+/* partial sum only (multi-GPU sharding): XYZZ coordinates, Montgomery limbs, 192 / 384 bytes.
+ * index_base is added to pair indices reported in d_status (global index of this shard). */
+EIP2537_ERROR bls12_b200_msm_partial_device(int group, const void* d_in, size_t n, uint64_t index_base,
+                                            void* d_partial, uint64_t* d_status, void* stream);
+/* sum `count` partials (e.g. after an NCCL all-gather), convert to affine and encode */
+EIP2537_ERROR bls12_b200_msm_combine_device(int group, const void* d_partials, int count, void* d_out,
+                                            void* stream);
+
+/* ---- device-resident pairing batch: d_in = concatenated calls, d_offsets[n+1] byte offsets,
+ *      d_outs n*32 bytes, d_errs n int32 codes.  Asynchronous on `stream`. */
+EIP2537_ERROR bls12_b200_pairing_batch_device(const void* d_in, const uint64_t* d_offsets, size_t n,
+                                              size_t total_pairs, void* d_outs, int32_t* d_errs, void* stream);
+
+/* ---- workload generators (synthetic inputs): out[i] = encode(k_i * generator),
+ *      k_i = 32-byte big-endian scalars.  Host buffers. */
+EIP2537_ERROR bls12_b200_g1_generator_mul(byte* out, const byte* scalars, size_t n);
+EIP2537_ERROR bls12_b200_g2_generator_mul(byte* out, const byte* scalars, size_t n);
+
+/* ---- K1 microbenchmarks: n_threads chains of `iters` dependent Fp multiplications; returns
+ *      elapsed milliseconds in *ms (CUDA events).  mode 0 = Fp mul, 1 = raw IMAD.WIDE peak probe */
+EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_c():
+    import c_oracle
+    c_oracle.lib()
+    return c_oracle
+
+
+@pytest.fixture(scope="session")
+def product():
+    """The product library through its public wrapper; fails loudly if the .so is missing."""
+    import blst_eip2537_b200 as b
+    b._native.lib()
+    return b

@@ -1,0 +1,190 @@
+// tests/host_emul/emul.cpp -- TEST ONLY.  Compiles the product's device functions (fp.cuh,
+// ec.cuh, codec.cuh, pairing.cuh: all B200_HD) for the HOST with g++, so their algorithms can
+// be checked against the oracle without a GPU.  The shipped library never contains this path
+// (engine.cu launches kernels only); on the host the portable 64-bit Fp multiply stands in for
+// the PTX carry-chain one, everything above it is the same source the GPU runs.
+#include <cstring>
+#include "../../blst_eip2537_b200/csrc/msm.cuh"
+#include "../../blst_eip2537_b200/csrc/pairing.cuh"
+
+using namespace b200;
+
+static void load_words(uint32_t* w, const unsigned char* in, int nwords) { memcpy(w, in, 4 * nwords); }
+
+template <class F> struct Node { XYZZ<F> s, w; };
+extern "C" {
+// r = a*b (canonical 48-byte big-endian in/out, via Montgomery form)
+void emul_fp_mul(unsigned char* out64, const unsigned char* a64, const unsigned char* b64) {
+  uint32_t w[16];
+  Fp a, b;
+  load_words(w, a64, 16); fp_from_slot(a, w);
+  load_words(w, b64, 16); fp_from_slot(b, w);
+  Fp r = mul(a, b);
+  fp_to_slot(w, r);
+  memcpy(out64, w, 64);
+}
+void emul_fp_inv(unsigned char* out64, const unsigned char* a64) {
+  uint32_t w[16];
+  Fp a;
+  load_words(w, a64, 16); fp_from_slot(a, w);
+  Fp r = inv(a);
+  fp_to_slot(w, r);
+  memcpy(out64, w, 64);
+}
+}  // extern C
+// straightforward MSM through the product's point code: sum k_i * P_i with per-point double-and-add
+template <class F>
+static int msm_simple(unsigned char* out, const unsigned char* in, size_t n) {
+  constexpr int PW = Wire<F>::POINT_WORDS, SW = Wire<F>::PAIR_WORDS;
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (size_t i = 0; i < n; i++) {
+    uint32_t w[SW];
+    load_words(w, in + 4 * SW * i, SW);
+    Affine<F> p;
+    int code = decode_point(p, w);
+    if (code) return code;
+    uint32_t k[8];
+    scalar_from_slot(k, w + PW);
+    XYZZ<F> t = xyzz_scalar_mul(p, k, 256);
+    xyzz_add(acc, t);
+  }
+  Affine<F> a = xyzz_to_affine(acc);
+  uint32_t w[PW];
+  encode_point(w, a);
+  memcpy(out, w, 4 * PW);
+  return 0;
+}
+extern "C" {
+int emul_g1_msm(unsigned char* out, const unsigned char* in, size_t n) { return msm_simple<Fp>(out, in, n); }
+int emul_g2_msm(unsigned char* out, const unsigned char* in, size_t n) { return msm_simple<Fp2>(out, in, n); }
+
+}  // extern C
+// host re-enactment of the Pippenger pipeline (same digit recoding, bucket layout, reduction tree
+// shapes and window combine as engine.cu's msm_pipeline), single-threaded
+template <class F>
+static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, int c) {
+  constexpr int PW = Wire<F>::POINT_WORDS, SW = Wire<F>::PAIR_WORDS;
+  MsmPlan plan = make_plan(c);
+  size_t nbt = (size_t)plan.nwin * plan.nb;
+  XYZZ<F>* buckets = new XYZZ<F>[nbt];
+  for (size_t b = 0; b < nbt; b++) buckets[b] = xyzz_inf<F>();
+  const uint32_t half = 1u << (plan.c - 1);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t w[SW];
+    load_words(w, in + 4 * SW * i, SW);
+    Affine<F> p;
+    int code = decode_point(p, w);
+    if (code) { delete[] buckets; return code; }
+    if (is_inf(p)) continue;
+    uint32_t k[8];
+    scalar_from_slot(k, w + PW);
+    uint32_t carry = 0;
+    for (int win = 0; win < plan.nwin; win++) {
+      int d;
+      auto bits = [&](int bit, int cc) {
+        int word = bit >> 5, sh = bit & 31;
+        uint32_t v = k[word] >> sh;
+        if (sh + cc > 32 && word + 1 < 8) v |= k[word + 1] << (32 - sh);
+        return v & ((1u << cc) - 1);
+      };
+      if (win < plan.nwin - 1) {
+        uint32_t raw_d = bits(win * plan.c, plan.c) + carry;
+        if (raw_d > half) { d = (int)raw_d - (int)(1u << plan.c); carry = 1; } else { d = (int)raw_d; carry = 0; }
+      } else d = (int)(bits(win * plan.c, plan.top_bits) + carry);
+      if (!d) continue;
+      uint32_t mag = d < 0 ? -d : d;
+      Affine<F> q = p;
+      if (d < 0) q.y = neg(q.y);
+      xyzz_madd(buckets[(size_t)win * plan.nb + mag - 1], q);
+    }
+  }
+  // reduction tree
+  int L0_log = plan.log_nb < 4 ? plan.log_nb : 4;
+  size_t npw = plan.nb >> L0_log;
+  Node<F>* cur = new Node<F>[plan.nwin * npw];
+  for (size_t t = 0; t < plan.nwin * npw; t++) {
+    int L = 1 << L0_log;
+    XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>();
+    for (int j = L - 1; j >= 0; j--) { xyzz_add(run, buckets[t * L + j]); xyzz_add(acc, run); }
+    cur[t].s = run; cur[t].w = acc;
+  }
+  int log_cov = L0_log;
+  while (npw > 1) {
+    int rem = plan.log_nb - log_cov, l_log = rem < 3 ? rem : 3, L = 1 << l_log;
+    size_t opw = npw >> l_log;
+    Node<F>* nxt = new Node<F>[plan.nwin * opw];
+    for (size_t t = 0; t < plan.nwin * opw; t++) {
+      XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>(), wsum = xyzz_inf<F>();
+      for (int j = L - 1; j >= 0; j--) { xyzz_add(wsum, cur[t * L + j].w); xyzz_add(acc, run); xyzz_add(run, cur[t * L + j].s); }
+      for (int q = 0; q < log_cov; q++) acc = xyzz_dbl(acc);
+      xyzz_add(wsum, acc);
+      nxt[t].s = run; nxt[t].w = wsum;
+    }
+    delete[] cur; cur = nxt; npw = opw; log_cov += l_log;
+  }
+  XYZZ<F> acc = cur[plan.nwin - 1].w;
+  for (int win = plan.nwin - 2; win >= 0; win--) {
+    for (int q = 0; q < plan.c; q++) acc = xyzz_dbl(acc);
+    xyzz_add(acc, cur[win].w);
+  }
+  Affine<F> a = xyzz_to_affine(acc);
+  uint32_t w[PW];
+  encode_point(w, a);
+  memcpy(out, w, 4 * PW);
+  delete[] cur; delete[] buckets;
+  return 0;
+}
+extern "C" {
+int emul_g1_pippenger(unsigned char* out, const unsigned char* in, size_t n, int c) { return msm_pippenger<Fp>(out, in, n, c); }
+int emul_g2_pippenger(unsigned char* out, const unsigned char* in, size_t n, int c) { return msm_pippenger<Fp2>(out, in, n, c); }
+
+// pairing call exactly as k_pairing_decode + k_pairing_calls do it; also dumps the GT element
+int emul_pairing(unsigned char* out32, unsigned char* gt576, const unsigned char* in, size_t k) {
+  Fp12 acc, cur;
+  for (size_t j = 0; j < k; j++) {
+    uint32_t w[96];
+    load_words(w, in + 384 * j, 96);
+    G1Affine p; G2Affine q;
+    int code = decode_point(p, w);
+    if (code == 0 && !g1_in_subgroup(p)) code = E_NOT_IN_SUBGROUP;
+    if (code) return code;
+    code = decode_point(q, w + 32);
+    if (code == 0 && !g2_in_subgroup(q)) code = E_NOT_IN_SUBGROUP;
+    if (code) return code;
+    if (j == 0) miller_loop(acc, p, q);
+    else { miller_loop(cur, p, q); fp12_mul(acc, acc, cur); }
+  }
+  final_exp(acc, acc);
+  memset(out32, 0, 32);
+  if (fp12_is_one(acc)) out32[31] = 1;
+  if (gt576) {
+    const Fp* e = reinterpret_cast<const Fp*>(&acc);
+    for (int i = 0; i < 12; i++) { uint32_t w[16]; fp_to_slot(w, e[i]); memcpy(gt576 + 48 * i, (unsigned char*)w + 16, 48); }
+  }
+  return 0;
+}
+int emul_g1_in_subgroup(const unsigned char* in128) {
+  uint32_t w[32]; load_words(w, in128, 32);
+  G1Affine p; int code = decode_point(p, w);
+  if (code) return -code;
+  return g1_in_subgroup(p) ? 1 : 0;
+}
+int emul_g2_in_subgroup(const unsigned char* in256) {
+  uint32_t w[64]; load_words(w, in256, 64);
+  G2Affine p; int code = decode_point(p, w);
+  if (code) return -code;
+  return g2_in_subgroup(p) ? 1 : 0;
+}
+int emul_g1_add(unsigned char* out, const unsigned char* in) {
+  uint32_t w[64]; load_words(w, in, 64);
+  G1Affine a, b;
+  int ca = decode_point(a, w), cb = decode_point(b, w + 32);
+  if (ca) return ca;
+  if (cb) return cb;
+  G1XYZZ acc = xyzz_from_affine(b);
+  xyzz_madd(acc, a);
+  G1Affine r = xyzz_to_affine(acc);
+  uint32_t o[32]; encode_point(o, r); memcpy(out, o, 128);
+  return 0;
+}
+}

@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle (bit-exact bytes and codes).
+
+Mirrors the reference's own test semantics: exact-byte success cases,
+specific error codes per failure class, dispatch/naive/bc entry points agree.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import py_oracle as po
+import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+G1B = po.encode_g1(po.G1)
+G2B = po.encode_g2(po.G2)
+ONES = (2 ** 256 - 1).to_bytes(32, "big")
+
+
+def be32(k):
+    return int(k).to_bytes(32, "big")
+
+
+def test_library_reports_cuda(product):
+    assert product._native.lib().bls12_b200_init(-1) == 0, product._native.lib().bls12_b200_last_error()
+
+
+def test_fp_mul_ptx_chain_matches_bigint(product):
+    """k_fp_chain: x0 = (R mod p) ^ tid-bit, x <- x*y (Montgomery) `iters` times; thread 0 digest."""
+    import ctypes
+    L = product._native.lib()
+    ms = ctypes.c_float()
+    dig = ctypes.create_string_buffer(48)
+    iters = 100
+    assert L.bls12_b200_fp_microbench(0, 256, iters, ctypes.byref(ms), dig) == 0
+    P = po.P
+    Rm = (1 << 384) % P
+    x = Rm  # montgomery one, thread 0 xor 0
+    y = po.G1_X * Rm % P
+    rinv = pow(1 << 384, -1, P)
+    for _ in range(iters):
+        x = x * y * rinv % P
+    assert int.from_bytes(dig.raw, "little") == x
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 17, 128, 1000])
+def test_g1_multiexp_random_matches_oracle(product, oracle_c, n):
+    data, _ = wl.g1_msm_input(n, 0x2537 + n)
+    err, ref = oracle_c.call("g1multiexp", data)
+    assert err == 0
+    assert product.G1Multiexp(data) == ref
+    assert product.G1MultiexpNaive(data) == ref
+    assert product.G1MultiexpBosCoster(data) == ref
+    if n == 1:
+        assert product.G1Mul(data) == ref
+
+
+@pytest.mark.parametrize("c", [3, 4, 7, 8, 11, 13, 16])
+def test_g1_multiexp_all_window_widths(product, oracle_c, c):
+    data, _ = wl.g1_msm_input(300, 0x9999)
+    _, ref = oracle_c.call("g1multiexp", data)
+    product.set_window(c)
+    try:
+        assert product.G1Multiexp(data) == ref
+    finally:
+        product.set_window(0)
+
+
+def test_g1_multiexp_closed_form_2_14(product, oracle_c):
+    n = 1 << 14
+    data, s = wl.g1_msm_input(n, 0x2537 + 1)
+    assert product.G1Multiexp(data) == oracle_c.g1_gen_mul(s)
+    err, ref = oracle_c.call("g1multiexp", data)   # Bos-Coster on the CPU, a few seconds
+    assert err == 0 and ref == oracle_c.g1_gen_mul(s)
+
+
+def test_g1_multiexp_adversarial(product, oracle_c):
+    neg_g = po.encode_g1(po.ec_neg(po.FP_OPS, po.G1))
+    order3 = po.encode_g1((0, 2))   # on E(Fp), NOT in G1: legal for MULTIEXP (eip2537.c:340)
+    data = (G1B + ONES + bytes(128) + ONES + G1B + bytes(32) + G1B + be32(5) + neg_g + be32(5)
+            + G1B + be32(7) + G1B + be32(7) + order3 + ONES + order3 + be32(po.R + 12345)
+            + G1B + be32(po.R) + G1B + be32(po.R - 1) + G1B + be32(1 << 255))
+    err, ref = oracle_c.call("g1multiexp", data)
+    assert err == 0
+    assert po.bls12_g1multiexp(data) == (0, ref)
+    for c in (0, 4, 8, 16):
+        product.set_window(c)
+        try:
+            assert product.G1Multiexp(data) == ref
+        finally:
+            product.set_window(0)
+    # all-infinity / zero scalars -> 128 zero bytes
+    assert product.G1Multiexp(bytes(160) * 3) == bytes(128)
+    assert product.G1Multiexp((G1B + bytes(32)) * 5) == bytes(128)
+    # same point many times with the same scalar: one bucket per window takes everything
+    rep = (G1B + be32(0xDEADBEEF12345)) * 200
+    assert product.G1Multiexp(rep) == oracle_c.call("g1multiexp", rep)[1]
+    # P and -P with equal scalars cancel
+    assert product.G1Multiexp(G1B + ONES + neg_g + ONES) == bytes(128)
+
+
+def test_g1_error_codes_and_precedence(product, oracle_c):
+    bad_pad = bytearray(G1B); bad_pad[3] = 1
+    ge_p = bytes(16) + po.P.to_bytes(48, "big") + G1B[64:]
+    off_curve = G1B[:64] + po.fp_to_bytes(5)
+    cases = [
+        (b"", 5), (G1B + ONES[:31], 5), (G1B + ONES + b"\x00", 5),
+        (bytes(bad_pad) + ONES, 3), (ge_p + ONES, 3), (off_curve + ONES, 1),
+        # first failing pair decides: off-curve (1) at index 1 beats invalid element (3) at index 2
+        (G1B + ONES + off_curve + ONES + ge_p + ONES, 1),
+        (G1B + ONES + ge_p + ONES + off_curve + ONES, 3),
+        # within a point INVALID_ELEMENT beats NOT_ON_CURVE: x invalid, y makes it off-curve anyway
+        (ge_p[:64] + po.fp_to_bytes(5) + ONES, 3),
+        # x = 0, y != 0 is not infinity: goes to the curve test
+        (po.fp_to_bytes(0) + po.fp_to_bytes(3) + ONES, 1),
+    ]
+    for data, code in cases:
+        for name in ("bls12_g1multiexp", "bls12_g1multiexp_naive", "bls12_g1multiexp_bc"):
+            got, out = product.raw_call(name, data, 128)
+            assert got == code, (name, len(data), got, code)
+            assert out is None
+        if data:
+            assert oracle_c.call("g1multiexp", data)[0] == code
+    # 6 pairs with the error late in a long input
+    many = (G1B + ONES) * 50 + off_curve + ONES + (G1B + ONES) * 10
+    assert product.raw_call("bls12_g1multiexp", many, 128)[0] == 1
+    assert product.raw_call("bls12_g1mul", G1B, 128)[0] == 5
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 33, 300])
+def test_g2_multiexp_random_matches_oracle(product, oracle_c, n):
+    data, _ = wl.g2_msm_input(n, 0x2537 + 100 + n)
+    err, ref = oracle_c.call("g2multiexp", data)
+    assert err == 0
+    assert product.G2Multiexp(data) == ref
+    assert product.G2MultiexpNaive(data) == ref
+    assert product.G2MultiexpBosCoster(data) == ref
+    if n == 1:
+        assert product.G2Mul(data) == ref
+
+
+def test_g2_adversarial_and_errors(product, oracle_c):
+    neg = po.encode_g2(po.ec_neg(po.F2_OPS, po.G2))
+    data = G2B + ONES + bytes(256) + ONES + G2B + bytes(32) + neg + be32(9) + G2B + be32(9) + G2B + be32(po.R + 5)
+    assert product.G2Multiexp(data) == oracle_c.call("g2multiexp", data)[1]
+    assert product.G2Multiexp(G2B + ONES + neg + ONES) == bytes(256)
+    off = G2B[:192] + po.fp_to_bytes(7)
+    bad = bytes(16) + po.P.to_bytes(48, "big") + G2B[64:]
+    for d, code in ((b"", 5), (G2B + ONES[:30], 5), (off + ONES, 1), (bad + ONES, 3), (G2B + ONES + off + ONES + bad + ONES, 1)):
+        assert product.raw_call("bls12_g2multiexp", d, 256)[0] == code
+
+
+def test_add_entry_points(product):
+    two_g = po.encode_g1(po.ec_add(po.FP_OPS, po.G1, po.G1))
+    assert product.G1Add(G1B + G1B) == two_g
+    assert product.G1Add(G1B + bytes(128)) == G1B
+    assert product.G1Add(G1B + po.encode_g1(po.ec_neg(po.FP_OPS, po.G1))) == bytes(128)
+    assert product.G2Add(G2B + G2B) == po.encode_g2(po.ec_add(po.F2_OPS, po.G2, po.G2))
+    assert product.raw_call("bls12_g1add", G1B, 128)[0] == 5
+
+
+def test_pairing_true_false_and_gt_semantics(product, oracle_c):
+    rng = wl.SplitMix64(77)
+    for k in (1, 2, 3, 5):
+        for truth in (True, False):
+            data = wl.pairing_call(k, rng, truth) if k > 1 else (G1B + G2B if not truth else bytes(128) + G2B)
+            err, ref = oracle_c.call("pairing", data)
+            assert err == 0
+            assert product.Pairing(data) == ref
+    # infinity members contribute 1
+    assert product.Pairing(bytes(384)) == bytes(31) + b"\x01"
+    assert product.Pairing(G1B + bytes(256)) == bytes(31) + b"\x01"
+    e_true = G1B + G2B + po.encode_g1(po.ec_neg(po.FP_OPS, po.G1)) + G2B
+    assert product.Pairing(e_true) == bytes(31) + b"\x01"
+    assert product.Pairing(e_true + bytes(384)) == bytes(31) + b"\x01"
+
+
+def test_pairing_error_codes_and_order(product, oracle_c):
+    order3 = po.encode_g1((0, 2))
+    off1 = G1B[:64] + po.fp_to_bytes(5)
+    off2 = G2B[:192] + po.fp_to_bytes(7)
+    bad1 = bytes(16) + po.P.to_bytes(48, "big") + G1B[64:]
+    cases = [
+        (b"", 5), (G1B + G2B[:255], 5),
+        (order3 + G2B, 2),            # on curve, not in G1 (invalid_subgroup_for_pairing semantics)
+        (off1 + G2B, 1), (bad1 + G2B, 3), (G1B + off2, 1),
+        (order3 + off2, 2),           # G1 subgroup failure comes before G2 decode
+        (off1 + off2, 1),
+        (G1B + G2B + order3 + G2B, 2),
+        (G1B + off2 + order3 + G2B, 1),   # first failing pair decides
+    ]
+    for data, code in cases:
+        got, out = product.raw_call("bls12_pairing", data, 32)
+        assert got == code, (len(data), got, code)
+        assert out is None
+        if data:
+            assert oracle_c.call("pairing", data)[0] == code
+
+
+def test_pairing_batch_matches_oracle(product, oracle_c):
+    data, offs, truth = wl.pairing_batch(40, 0x2537 + 4, kmin=2, kmax=6)
+    outs, errs = product.PairingBatch(data, offs)
+    assert list(errs) == [0] * 40
+    assert [int(o[31]) for o in outs] == [1 if t else 0 for t in truth]
+    for j in range(40):
+        assert oracle_c.call("pairing", data[offs[j]:offs[j + 1]]) == (0, bytes(outs[j]))
+    # a batch with failing and malformed calls keeps per-call codes
+    order3 = po.encode_g1((0, 2))
+    calls = [data[offs[0]:offs[1]], order3 + G2B, b"", G1B + G2B[:100], data[offs[1]:offs[2]]]
+    blob = b"".join(calls)
+    o2 = [0]
+    for cdata in calls:
+        o2.append(o2[-1] + len(cdata))
+    outs, errs = product.PairingBatch(blob, o2)
+    assert list(errs) == [0, 2, 5, 5, 0]
+    assert bytes(outs[0]) == oracle_c.call("pairing", calls[0])[1]
+    assert bytes(outs[4]) == oracle_c.call("pairing", calls[4])[1]
+    assert bytes(outs[1]) == bytes(32)
+
+
+def test_g2_subgroup_rejection_in_pairing(product, oracle_c):
+    """A point on E'(Fp2) outside G2 must give code 2 (found by hashing x until on-curve)."""
+    rnd = random.Random(11)
+    while True:
+        x = (rnd.randrange(po.P), rnd.randrange(po.P))
+        rhs = po.f2_add(po.f2_mul(po.f2_sqr(x), x), (4, 4))
+        # sqrt in Fp2 via norm trick
+        n = (rhs[0] * rhs[0] + rhs[1] * rhs[1]) % po.P
+        s = pow(n, (po.P + 1) // 4, po.P)
+        if s * s % po.P != n:
+            continue
+        y = None
+        for sg in (s, -s % po.P):
+            t = (rhs[0] + sg) * po.INV2 % po.P
+            xr = pow(t, (po.P + 1) // 4, po.P)
+            if xr * xr % po.P == t and xr:
+                yi = rhs[1] * po.fp_inv(2 * xr % po.P) % po.P
+                if po.f2_sqr((xr, yi)) == rhs:
+                    y = (xr, yi)
+                    break
+        if y:
+            break
+    q = po.encode_g2((x, y))
+    assert oracle_c.call("pairing", G1B + q)[0] == 2
+    assert product.raw_call("bls12_pairing", G1B + q, 32)[0] == 2
+    # ... but it is a legal MULTIEXP input
+    assert product.G2Multiexp(q + ONES) == oracle_c.call("g2multiexp", q + ONES)[1]

@@ -1,0 +1,59 @@
+#!/usr/bin/env python3
+"""Ad-hoc timing probe (developer tool, not the contract bench): K1 microbenchmarks and MSM/pairing timings."""
+import ctypes
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import blst_eip2537_b200 as b
+
+L = b._native.lib()
+assert L.bls12_b200_init(-1) == 0, L.bls12_b200_last_error()
+ms = ctypes.c_float()
+what = sys.argv[1:] or ["micro", "msm", "pairing"]
+
+if "micro" in what:
+    nthr = 148 * 2048
+    for mode, name, per in ((1, "imad.wide", 64), (0, "fp_mul", 1)):
+        iters = 2000 if mode == 1 else 1000
+        L.bls12_b200_fp_microbench(mode, nthr, iters, ctypes.byref(ms), None)
+        ops = nthr * iters * per
+        print("%s: %.3f ms, %.3e ops/s" % (name, ms.value, ops / (ms.value * 1e-3)), flush=True)
+
+R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+rng = np.random.default_rng(0x2537)
+
+
+def gen_g1(n):
+    sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 0] &= 0x3F   # < 2^254 < r
+    pts = np.frombuffer(b.generator_mul(1, sc), dtype=np.uint8).reshape(n, 128)
+    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    return np.concatenate([pts, ks], axis=1).reshape(-1)
+
+
+if "msm" in what:
+    for logn in (10, 14, 16, 18, 20):
+        n = 1 << logn
+        t0 = time.time(); data = gen_g1(n); tg = time.time() - t0
+        h = torch.from_numpy(data).pin_memory()
+        for rep in range(3):
+            t0 = time.time(); out = b.G1Multiexp(h); dt = time.time() - t0
+        d_in = h.cuda()
+        d_out = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        d_st = torch.zeros(1, dtype=torch.int64, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        for c in ((0,) if logn < 16 else (0, 12, 13, 14, 15, 16)):
+            b.set_window(c)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for rep in range(3):
+                ev0.record()
+                assert L.bls12_b200_msm_device(1, d_in.data_ptr(), n, d_out.data_ptr(), d_st.data_ptr(), s) == 0
+                ev1.record(); torch.cuda.synchronize()
+            assert bytes(d_out.cpu().numpy()) == out and d_st.item() == -1
+            print("G1 MSM 2^%d c=%d: gen %.2fs  e2e %.2f ms  device %.3f ms  -> %.3e pts/s" % (logn, c, tg, dt * 1e3, ev0.elapsed_time(ev1), n / (ev0.elapsed_time(ev1) * 1e-3)), flush=True)
+        b.set_window(0)
