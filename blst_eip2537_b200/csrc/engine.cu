@@ -228,7 +228,7 @@ static int msm_partial_device_impl(const void* d_in, size_t n, uint64_t index_ba
   if (rc) return rc;
   Engine& e = *ep;
   std::lock_guard<std::mutex> lk(e.mu);
-  cudaStream_t s = stream ? (cudaStream_t)stream : e.stream;
+  cudaStream_t s = (cudaStream_t)stream;
   if (((uintptr_t)d_in & 15) || ((uintptr_t)d_partial & 15)) {
     snprintf(g_last_error, sizeof g_last_error, "device pointers must be 16-byte aligned");
     return E_MEMORY;
@@ -248,7 +248,7 @@ extern "C" EIP2537_ERROR bls12_b200_msm_combine_device(int group, const void* d_
   Engine* ep;
   int rc = engine_get(&ep, -1);
   if (rc) return (EIP2537_ERROR)rc;
-  cudaStream_t s = stream ? (cudaStream_t)stream : ep->stream;
+  cudaStream_t s = (cudaStream_t)stream;
   if (group == 1) LAUNCH(k_finalize<Fp>, 1, 32, s, (const XYZZ<Fp>*)d_partials, count, (uint32_t*)d_out);
   else            LAUNCH(k_finalize<Fp2>, 1, 32, s, (const XYZZ<Fp2>*)d_partials, count, (uint32_t*)d_out);
   if (cudaGetLastError() != cudaSuccess) return EIP2537_MEMORY_ERROR;
@@ -265,7 +265,7 @@ extern "C" EIP2537_ERROR bls12_b200_msm_device(int group, const void* d_in, size
     std::lock_guard<std::mutex> lk(ep->mu);
     if ((rc = ep->partial.reserve(sizeof(XYZZ<Fp2>)))) return (EIP2537_ERROR)rc;
   }
-  cudaStream_t s = stream ? (cudaStream_t)stream : ep->stream;
+  cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(d_status, 0xFF, 8, s) != cudaSuccess) return EIP2537_MEMORY_ERROR;
   EIP2537_ERROR r = bls12_b200_msm_partial_device(group, d_in, n, 0, ep->partial.ptr, d_status, (void*)s);
   if (r) return r;
@@ -389,7 +389,7 @@ extern "C" EIP2537_ERROR bls12_b200_pairing_batch_device(const void* d_in, const
   int rc = engine_get(&ep, -1);
   if (rc) return (EIP2537_ERROR)rc;
   std::lock_guard<std::mutex> lk(ep->mu);
-  cudaStream_t s = stream ? (cudaStream_t)stream : ep->stream;
+  cudaStream_t s = (cudaStream_t)stream;
   return (EIP2537_ERROR)pairing_batch_device_impl(*ep, (const uint32_t*)d_in, (const unsigned long long*)d_offsets, n,
                                                   total_pairs, (uint32_t*)d_outs, (int*)d_errs, s);
 }
@@ -521,6 +521,60 @@ extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, in
   if (digest48) CUDA_TRY2(cudaMemcpy(digest48, e.pts.ptr, 48, cudaMemcpyDeviceToHost));
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
+  return EIP2537_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------
+// on-device self test: PTX carry-chain field ops vs portable 64-bit C++ on the same inputs
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fp st_add_ref(const Fp& a, const Fp& b, bool subtract) {
+  const uint32_t* p = C_P();
+  uint32_t t[12];
+  uint64_t c = 0;
+  if (!subtract) {
+    for (int i = 0; i < 12; i++) { uint64_t s = (uint64_t)a.v[i] + b.v[i] + c; t[i] = (uint32_t)s; c = s >> 32; }
+    uint32_t u[12]; uint64_t bw = 0;
+    for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)t[i] - p[i] - bw; u[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+    Fp r; for (int i = 0; i < 12; i++) r.v[i] = bw ? t[i] : u[i];
+    return r;
+  }
+  uint64_t bw = 0;
+  for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - bw; t[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+  if (bw) { c = 0; for (int i = 0; i < 12; i++) { uint64_t s = (uint64_t)t[i] + p[i] + c; t[i] = (uint32_t)s; c = s >> 32; } }
+  Fp r; for (int i = 0; i < 12; i++) r.v[i] = t[i];
+  return r;
+}
+__global__ void __launch_bounds__(128) k_selftest(size_t n, unsigned long long* mismatches) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // two pseudo-random field elements (< p: top limb masked below p's top limb 0x1a0111ea)
+  unsigned long long s = 0x9E3779B97F4A7C15ull * (i + 1);
+  Fp a, b;
+  for (int k = 0; k < 12; k++) {
+    s ^= s >> 12; s ^= s << 25; s ^= s >> 27; a.v[k] = (uint32_t)((s * 0x2545F4914F6CDD1Dull) >> 32);
+    s ^= s >> 12; s ^= s << 25; s ^= s >> 27; b.v[k] = (uint32_t)((s * 0x2545F4914F6CDD1Dull) >> 32);
+  }
+  a.v[11] &= 0x0fffffffu; b.v[11] &= 0x0fffffffu;
+  if ((i & 7) == 0) { a = fp_load_const(C_P()); a.v[0] -= 1; }            // p - 1
+  if ((i & 7) == 1) { b = fp_zero(); }
+  if ((i & 7) == 2) { b = a; }
+  if (!eq(mul(a, b), mul_portable(a, b))) atomicAdd(&mismatches[0], 1ull);
+  if (!eq(add(a, b), st_add_ref(a, b, false))) atomicAdd(&mismatches[1], 1ull);
+  if (!eq(sub(a, b), st_add_ref(a, b, true))) atomicAdd(&mismatches[2], 1ull);
+  Fp q = mul(a, b);
+  if (!is_zero(a) && !is_zero(b) && (i & 63) == 5) { if (!eq(mul(mul(q, inv(b)), fp_load_const(C_RR())), mul(a, fp_load_const(C_RR())))) atomicAdd(&mismatches[3], 1ull); }
+}
+extern "C" EIP2537_ERROR bls12_b200_selftest(uint64_t* mismatches4, size_t n) {
+  Engine* ep;
+  int rc = engine_get(&ep, -1);
+  if (rc) return (EIP2537_ERROR)rc;
+  Engine& e = *ep;
+  std::lock_guard<std::mutex> lk(e.mu);
+  if ((rc = e.status.reserve(64))) return (EIP2537_ERROR)rc;
+  CUDA_TRY2(cudaMemsetAsync(e.status.ptr, 0, 32, e.stream));
+  LAUNCH(k_selftest, blocks_for(n, 128), 128, e.stream, n, (unsigned long long*)e.status.ptr);
+  CUDA_TRY2(cudaMemcpyAsync(mismatches4, e.status.ptr, 32, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY2(cudaStreamSynchronize(e.stream));
   return EIP2537_SUCCESS;
 }
 

@@ -68,16 +68,29 @@ B200_HD bool eq(const Fp& a, const Fp& b) {
 
 // r = a - p if a >= p else a        (a < 2p; `top` is an extra carry word of a)
 B200_HD Fp fp_reduce_once(const Fp& a, uint32_t top) {
-  const uint32_t* p = C_P();
   Fp t;
   uint32_t borrow;
 #if defined(__CUDA_ARCH__)
-  asm("sub.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(a.v[0]), "r"(p[0]));
-#pragma unroll
-  for (int i = 1; i < 12; i++) asm("subc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(a.v[i]), "r"(p[i]));
-  asm("subc.u32 %0, %1, 0;" : "=r"(borrow) : "r"(top));   // borrow = top - 0 - B  (0 or -1 when top = 0)
+  // one asm statement per carry chain: the CC flag must not be separated from its consumers
+  asm(
+      "sub.cc.u32 %0, %13, %26;\n\t"
+      "subc.cc.u32 %1, %14, %27;\n\t"
+      "subc.cc.u32 %2, %15, %28;\n\t"
+      "subc.cc.u32 %3, %16, %29;\n\t"
+      "subc.cc.u32 %4, %17, %30;\n\t"
+      "subc.cc.u32 %5, %18, %31;\n\t"
+      "subc.cc.u32 %6, %19, %32;\n\t"
+      "subc.cc.u32 %7, %20, %33;\n\t"
+      "subc.cc.u32 %8, %21, %34;\n\t"
+      "subc.cc.u32 %9, %22, %35;\n\t"
+      "subc.cc.u32 %10, %23, %36;\n\t"
+      "subc.cc.u32 %11, %24, %37;\n\t"
+      "subc.u32 %12, %25, 0;"
+      : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]), "=r"(t.v[6]), "=r"(t.v[7]), "=r"(t.v[8]), "=r"(t.v[9]), "=r"(t.v[10]), "=r"(t.v[11]), "=r"(borrow)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(top), "n"(B200_P0), "n"(B200_P1), "n"(B200_P2), "n"(B200_P3), "n"(B200_P4), "n"(B200_P5), "n"(B200_P6), "n"(B200_P7), "n"(B200_P8), "n"(B200_P9), "n"(B200_P10), "n"(B200_P11));
   bool keep_a = (borrow >> 31) != 0;                        // went negative => a < p
 #else
+  const uint32_t* p = C_P();
   uint64_t b = 0;
   for (int i = 0; i < 12; i++) {
     uint64_t d = (uint64_t)a.v[i] - p[i] - b;
@@ -96,9 +109,21 @@ B200_HD Fp fp_reduce_once(const Fp& a, uint32_t top) {
 B200_HD Fp add(const Fp& a, const Fp& b) {
   Fp t;
 #if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
-#pragma unroll
-  for (int i = 1; i < 12; i++) asm("addc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+  asm(
+      "add.cc.u32 %0, %12, %24;\n\t"
+      "addc.cc.u32 %1, %13, %25;\n\t"
+      "addc.cc.u32 %2, %14, %26;\n\t"
+      "addc.cc.u32 %3, %15, %27;\n\t"
+      "addc.cc.u32 %4, %16, %28;\n\t"
+      "addc.cc.u32 %5, %17, %29;\n\t"
+      "addc.cc.u32 %6, %18, %30;\n\t"
+      "addc.cc.u32 %7, %19, %31;\n\t"
+      "addc.cc.u32 %8, %20, %32;\n\t"
+      "addc.cc.u32 %9, %21, %33;\n\t"
+      "addc.cc.u32 %10, %22, %34;\n\t"
+      "addc.u32 %11, %23, %35;"
+      : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]), "=r"(t.v[6]), "=r"(t.v[7]), "=r"(t.v[8]), "=r"(t.v[9]), "=r"(t.v[10]), "=r"(t.v[11])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]), "r"(b.v[8]), "r"(b.v[9]), "r"(b.v[10]), "r"(b.v[11]));
   // p < 2^381: a + b < 2^382 never carries out of 12 limbs
 #else
   uint64_t c = 0;
@@ -112,17 +137,40 @@ B200_HD Fp add(const Fp& a, const Fp& b) {
 }
 
 B200_HD Fp sub(const Fp& a, const Fp& b) {
-  const uint32_t* p = C_P();
   Fp t;
 #if defined(__CUDA_ARCH__)
   uint32_t mask;
-  asm("sub.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
-#pragma unroll
-  for (int i = 1; i < 12; i++) asm("subc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
-  asm("subc.u32 %0, 0, 0;" : "=r"(mask));   // 0 or 0xffffffff
-  asm("add.cc.u32 %0, %1, %2;" : "=r"(t.v[0]) : "r"(t.v[0]), "r"(p[0] & mask));
-#pragma unroll
-  for (int i = 1; i < 12; i++) asm("addc.cc.u32 %0, %1, %2;" : "=r"(t.v[i]) : "r"(t.v[i]), "r"(p[i] & mask));
+  asm(
+      "sub.cc.u32 %0, %13, %25;\n\t"
+      "subc.cc.u32 %1, %14, %26;\n\t"
+      "subc.cc.u32 %2, %15, %27;\n\t"
+      "subc.cc.u32 %3, %16, %28;\n\t"
+      "subc.cc.u32 %4, %17, %29;\n\t"
+      "subc.cc.u32 %5, %18, %30;\n\t"
+      "subc.cc.u32 %6, %19, %31;\n\t"
+      "subc.cc.u32 %7, %20, %32;\n\t"
+      "subc.cc.u32 %8, %21, %33;\n\t"
+      "subc.cc.u32 %9, %22, %34;\n\t"
+      "subc.cc.u32 %10, %23, %35;\n\t"
+      "subc.cc.u32 %11, %24, %36;\n\t"
+      "subc.u32 %12, 0, 0;"
+      : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]), "=r"(t.v[6]), "=r"(t.v[7]), "=r"(t.v[8]), "=r"(t.v[9]), "=r"(t.v[10]), "=r"(t.v[11]), "=r"(mask)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]), "r"(b.v[8]), "r"(b.v[9]), "r"(b.v[10]), "r"(b.v[11]));
+  asm(
+      "add.cc.u32 %0, %0, %12;\n\t"
+      "addc.cc.u32 %1, %1, %13;\n\t"
+      "addc.cc.u32 %2, %2, %14;\n\t"
+      "addc.cc.u32 %3, %3, %15;\n\t"
+      "addc.cc.u32 %4, %4, %16;\n\t"
+      "addc.cc.u32 %5, %5, %17;\n\t"
+      "addc.cc.u32 %6, %6, %18;\n\t"
+      "addc.cc.u32 %7, %7, %19;\n\t"
+      "addc.cc.u32 %8, %8, %20;\n\t"
+      "addc.cc.u32 %9, %9, %21;\n\t"
+      "addc.cc.u32 %10, %10, %22;\n\t"
+      "addc.u32 %11, %11, %23;"
+      : "+r"(t.v[0]), "+r"(t.v[1]), "+r"(t.v[2]), "+r"(t.v[3]), "+r"(t.v[4]), "+r"(t.v[5]), "+r"(t.v[6]), "+r"(t.v[7]), "+r"(t.v[8]), "+r"(t.v[9]), "+r"(t.v[10]), "+r"(t.v[11])
+      : "r"(B200_P0 & mask), "r"(B200_P1 & mask), "r"(B200_P2 & mask), "r"(B200_P3 & mask), "r"(B200_P4 & mask), "r"(B200_P5 & mask), "r"(B200_P6 & mask), "r"(B200_P7 & mask), "r"(B200_P8 & mask), "r"(B200_P9 & mask), "r"(B200_P10 & mask), "r"(B200_P11 & mask));
 #else
   uint64_t bw = 0;
   for (int i = 0; i < 12; i++) {
@@ -131,6 +179,7 @@ B200_HD Fp sub(const Fp& a, const Fp& b) {
     bw = (d >> 32) & 1;
   }
   if (bw) {
+    const uint32_t* p = C_P();
     uint64_t c = 0;
     for (int i = 0; i < 12; i++) {
       uint64_t s = (uint64_t)t.v[i] + p[i] + c;
@@ -251,7 +300,9 @@ B200_D Fp mul(const Fp& a, const Fp& b) {
   return fp_reduce_once(r, x[12]);
 }
 #else
-B200_HD Fp mul(const Fp& a, const Fp& b) {
+B200_HD Fp mul(const Fp& a, const Fp& b);
+#endif
+B200_HD Fp mul_portable(const Fp& a, const Fp& b) {
   const uint32_t* p = C_P();
   uint32_t t[14];
 #pragma unroll
@@ -286,6 +337,8 @@ B200_HD Fp mul(const Fp& a, const Fp& b) {
   for (int i = 0; i < 12; i++) r.v[i] = t[i];
   return fp_reduce_once(r, t[12]);
 }
+#if !(defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE))
+B200_HD Fp mul(const Fp& a, const Fp& b) { return mul_portable(a, b); }
 #endif
 B200_HD Fp sqr(const Fp& a) { return mul(a, a); }
 

@@ -9,7 +9,8 @@
  * identical to the single-call function of eip2537.h (same bytes, same codes).
  *
  * All pointers named d_* are CUDA device pointers, 16-byte aligned, on the current device.
- * `stream` is a cudaStream_t passed as void* (NULL = the engine's own stream).
+ * `stream` is a cudaStream_t passed as void* and used as given (NULL = the CUDA default stream);
+ * work submitted through these entry points is asynchronous with respect to the host.
  * Every function returns an EIP2537_ERROR; CUDA failures map to EIP2537_MEMORY_ERROR.
  */
 #ifndef __EIP2537_B200_H__
@@ -64,6 +65,10 @@ EIP2537_ERROR bls12_b200_g2_generator_mul(byte* out, const byte* scalars, size_t
 /* ---- K1 microbenchmarks: n_threads chains of `iters` dependent Fp multiplications; returns
  *      elapsed milliseconds in *ms (CUDA events).  mode 0 = Fp mul, 1 = raw IMAD.WIDE peak probe */
 EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48);
+
+/* ---- on-device self test of the PTX field arithmetic against portable C++ on n pseudo-random
+ *      inputs; mismatches4 = {mul, add, sub, inv} mismatch counts (all must be 0) */
+EIP2537_ERROR bls12_b200_selftest(uint64_t* mismatches4, size_t n);
 
 #ifdef __cplusplus
 }

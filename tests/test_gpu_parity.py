@@ -26,6 +26,12 @@ def test_library_reports_cuda(product):
     assert product._native.lib().bls12_b200_init(-1) == 0, product._native.lib().bls12_b200_last_error()
 
 
+def test_ptx_field_ops_match_portable_on_device(product):
+    m = np.zeros(4, dtype=np.uint64)
+    assert product._native.lib().bls12_b200_selftest(m.ctypes.data, 1 << 16) == 0
+    assert list(m) == [0, 0, 0, 0], "mismatches mul/add/sub/inv: %s" % list(m)
+
+
 def test_fp_mul_ptx_chain_matches_bigint(product):
     """k_fp_chain: x0 = (R mod p) ^ tid-bit, x <- x*y (Montgomery) `iters` times; thread 0 digest."""
     import ctypes

@@ -47,6 +47,7 @@ if "msm" in what:
         d_out = torch.zeros(128, dtype=torch.uint8, device="cuda")
         d_st = torch.zeros(1, dtype=torch.int64, device="cuda")
         s = torch.cuda.current_stream().cuda_stream
+        torch.cuda.synchronize()
         for c in ((0,) if logn < 16 else (0, 12, 13, 14, 15, 16)):
             b.set_window(c)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,3 +58,19 @@ if "msm" in what:
             assert bytes(d_out.cpu().numpy()) == out and d_st.item() == -1
             print("G1 MSM 2^%d c=%d: gen %.2fs  e2e %.2f ms  device %.3f ms  -> %.3e pts/s" % (logn, c, tg, dt * 1e3, ev0.elapsed_time(ev1), n / (ev0.elapsed_time(ev1) * 1e-3)), flush=True)
         b.set_window(0)
+
+if "pairing" in what:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import workloads as wl
+    data, offs, truth = wl.pairing_batch(64, 99, 2, 16)
+    reps = 64
+    blob = data * reps
+    o = [0]
+    for r in range(reps):
+        for j in range(64):
+            o.append(o[-1] + offs[j + 1] - offs[j])
+    for rep in range(3):
+        t0 = time.time(); outs, errs = b.PairingBatch(blob, o); dt = time.time() - t0
+    assert [int(x[31]) for x in outs[:64]] == [1 if t else 0 for t in truth] and not errs.any()
+    print("pairing batch %d calls (%d pairs): %.1f ms -> %.0f checks/s" % (len(o) - 1, len(blob) // 384, dt * 1e3, (len(o) - 1) / dt), flush=True)
