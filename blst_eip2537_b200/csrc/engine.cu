@@ -114,18 +114,29 @@ static int engine_get(Engine** out, int device) {
 static int choose_window(size_t n) {
   int forced = g_forced_window.load();
   if (forced >= 2 && forced <= 16) return forced;
-  double best = 1e300;
-  int best_c = 4;
-  for (int c = 3; c <= 16; c++) {
-    MsmPlan p = make_plan(c);
-    double used = 0;  // buckets actually populated
-    used += (double)(p.nwin - 1) * (double)(1u << (c - 1)) + (double)(1u << p.top_bits);
-    double cost = 10.0 * (double)n * p.nwin + 28.0 * used + 9.0 * c * (p.nwin - 1)
-                  + 2000.0 * p.log_nb;  // serial tree depth costs latency, not throughput
-    if (cost < best) { best = cost; best_c = c; }
-  }
-  return best_c;
+  // Widths dividing 256 give a full-width top window, so no window degenerates into a handful of
+  // huge buckets (the top window is unsigned: it absorbs the last signed-digit carry).
+  if (n < 32) return 4;
+  if (n < (1u << 15)) return 8;
+  return 16;
 }
+
+// optional per-stage timing (bench.py's roofline leg): events around the stages of the last MSM
+static std::atomic<int> g_profile{0};
+struct StageTimer {
+  static constexpr int N = 8;
+  cudaEvent_t ev[N] = {};
+  bool made = false;
+  int used = 0;
+  void mark(int i, cudaStream_t s) {
+    if (!g_profile.load()) return;
+    if (!made) { for (int k = 0; k < N; k++) cudaEventCreate(&ev[k]); made = true; }
+    cudaEventRecord(ev[i], s);
+    if (i + 1 > used) used = i + 1;
+  }
+};
+static StageTimer g_stage;
+static unsigned long long g_last_entries = 0;
 
 template <class F>
 static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t index_base, XYZZ<F>* d_partial,
@@ -150,6 +161,7 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
   uint32_t* entries = (uint32_t*)e.entries.ptr;
   XYZZ<F>* buckets = (XYZZ<F>*)e.buckets.ptr;
 
+  g_stage.mark(0, s);
   CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * nbt * sizeof(uint32_t), s));
   LAUNCH(k_decode<F>, blocks_for(n, 128), 128, s, d_raw, n, pts, d_status, (size_t)index_base);
   LAUNCH(k_digits<F>, blocks_for(n, 256), 256, s, d_raw, n, pts, plan, digits, counts);
@@ -158,7 +170,16 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
   LAUNCH(k_scan_sums, 1, 1024, s, block_sums, nblk);
   LAUNCH(k_scan_fix, nblk, 1024, s, offsets, block_sums, (uint32_t)nbt);
   LAUNCH(k_scatter, blocks_for(n * plan.nwin, 256), 256, s, digits, n, plan, offsets, cursors, entries);
+  g_stage.mark(1, s);
   LAUNCH(k_accumulate<F>, blocks_for(nbt, 128), 128, s, pts, entries, offsets, counts, (uint32_t)nbt, buckets);
+  g_stage.mark(2, s);
+  if (g_profile.load()) {   // total sorted entries = non-zero digits D (algorithmic work of k_accumulate)
+    uint32_t last_off = 0, last_cnt = 0;
+    cudaMemcpyAsync(&last_off, offsets + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&last_cnt, counts + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    g_last_entries = (unsigned long long)last_off + last_cnt;
+  }
 
   // reduction tree: leaf folds L0 buckets, inner levels fold L children
   int log_cov = 0;                       // log2(buckets covered per node)
@@ -181,7 +202,9 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
     nodes_per_win = out_per_win;
     log_cov += l_log;
   }
+  g_stage.mark(3, s);
   LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan, d_partial);
+  g_stage.mark(4, s);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
 }
@@ -606,3 +629,12 @@ extern "C" void bls12_b200_shutdown(void) {
 extern "C" const char* bls12_b200_last_error(void) { return g_last_error; }
 extern "C" uint64_t bls12_b200_launch_count(void) { return g_launches.load(); }
 extern "C" void bls12_b200_set_window(int c) { g_forced_window.store(c); }
+extern "C" void bls12_b200_set_profile(int on) { g_profile.store(on); }
+// stage_ms[4] = {decode+digits+sort, accumulate, bucket reduce tree, window combine} of the last profiled MSM
+extern "C" EIP2537_ERROR bls12_b200_last_msm_profile(float* stage_ms4, uint64_t* nonzero_digits) {
+  if (g_stage.used < 5) return EIP2537_EMPTY_INPUT;
+  CUDA_TRY2(cudaEventSynchronize(g_stage.ev[4]));
+  for (int i = 0; i < 4; i++) CUDA_TRY2(cudaEventElapsedTime(&stage_ms4[i], g_stage.ev[i], g_stage.ev[i + 1]));
+  *nonzero_digits = g_last_entries;
+  return EIP2537_SUCCESS;
+}

@@ -66,6 +66,13 @@ EIP2537_ERROR bls12_b200_g2_generator_mul(byte* out, const byte* scalars, size_t
  *      elapsed milliseconds in *ms (CUDA events).  mode 0 = Fp mul, 1 = raw IMAD.WIDE peak probe */
 EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48);
 
+/* ---- per-stage timing of the MSM pipeline (CUDA events on the launching stream), for the
+ *      roofline report: enable, run one bls12_b200_msm_device, then read
+ *      stage_ms4 = {decode+digits+sort, bucket accumulate, bucket reduce tree, window combine}
+ *      and the number of non-zero signed digits (= point additions done by the accumulate kernel) */
+void bls12_b200_set_profile(int on);
+EIP2537_ERROR bls12_b200_last_msm_profile(float* stage_ms4, uint64_t* nonzero_digits);
+
 /* ---- on-device self test of the PTX field arithmetic against portable C++ on n pseudo-random
  *      inputs; mismatches4 = {mul, add, sub, inv} mismatch counts (all must be 0) */
 EIP2537_ERROR bls12_b200_selftest(uint64_t* mismatches4, size_t n);

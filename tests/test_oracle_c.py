@@ -1,0 +1,89 @@
+"""Pins the C oracle (restated reference) against the big-int model and the golden fixtures."""
+import random
+
+import pytest
+
+import py_oracle as o
+import vectors
+
+
+def be32(k):
+    return int(k).to_bytes(32, "big")
+
+
+def test_generator_multiples(oracle_c):
+    rnd = random.Random(3)
+    for k in (0, 1, 2, o.R - 1, o.R, rnd.randrange(1 << 256)):
+        assert oracle_c.g1_gen_mul(k) == o.encode_g1(o.ec_mul(o.FP_OPS, k, o.G1))
+    k = rnd.randrange(1 << 256)
+    assert oracle_c.g2_gen_mul(k) == o.encode_g2(o.ec_mul(o.F2_OPS, k, o.G2))
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 9, 40])
+def test_msm_strategies_agree_with_bigint(oracle_c, n):
+    """dispatch / naive / Bos-Coster must agree (the reference's own differential test, src/test.c:208-228)."""
+    rnd = random.Random(100 + n)
+    d1 = b"".join(oracle_c.g1_gen_mul(rnd.randrange(o.R)) + be32(rnd.randrange(1 << 256)) for _ in range(n))
+    want = o.bls12_g1multiexp(d1)
+    for name in ("g1multiexp", "g1multiexp_naive", "g1multiexp_bc"):
+        assert oracle_c.call(name, d1) == want
+    if n <= 9:
+        d2 = b"".join(oracle_c.g2_gen_mul(rnd.randrange(o.R)) + be32(rnd.randrange(1 << 256)) for _ in range(n))
+        want = o.bls12_g2multiexp(d2)
+        for name in ("g2multiexp", "g2multiexp_naive", "g2multiexp_bc"):
+            assert oracle_c.call(name, d2) == want
+
+
+def test_bos_coster_wide_gap_path(oracle_c):
+    """scalars with > 6 bits of gap force the `skipped_result` branch (eip2537.c:178-191)."""
+    g = o.encode_g1(o.G1)
+    h = oracle_c.g1_gen_mul(7)
+    data = g + be32((1 << 255) + 12345) + h + be32(3) + g + be32(1 << 200) + h + be32(2) + g + be32(1) + h + bytes(32)
+    want = o.bls12_g1multiexp(data)
+    assert oracle_c.call("g1multiexp_bc", data) == want
+    assert oracle_c.call("g1multiexp", data) == want
+
+
+def test_pairing_gt_element_matches_bigint(oracle_c):
+    rnd = random.Random(5)
+    a, b = rnd.randrange(o.R), rnd.randrange(o.R)
+    data = oracle_c.g1_gen_mul(a) + oracle_c.g2_gen_mul(b)
+    err, gt = oracle_c.pairing_gt(data)
+    ref = o.final_exp(o.miller_loop_pairs([(o.ec_mul(o.FP_OPS, a, o.G1), o.ec_mul(o.F2_OPS, b, o.G2))]))
+    flat = [c for h in ref for f2 in h for c in f2]
+    assert err == 0 and gt == b"".join(x.to_bytes(48, "big") for x in flat)
+
+
+def test_subgroup_checks_fast_vs_naive(oracle_c):
+    rnd = random.Random(9)
+    pts = [o.encode_g1((0, 2)), o.encode_g1(o.G1), bytes(128), oracle_c.g1_gen_mul(rnd.randrange(o.R))]
+    while len(pts) < 8:
+        x = rnd.randrange(o.P)
+        y = pow((x ** 3 + 4) % o.P, (o.P + 1) // 4, o.P)
+        if y * y % o.P == (x ** 3 + 4) % o.P:
+            pts.append(o.encode_g1((x, y)))
+    for p in pts:
+        assert oracle_c.lib().oracle_g1_in_subgroup(p, 0) == oracle_c.lib().oracle_g1_in_subgroup(p, 1)
+    for q in (o.encode_g2(o.G2), bytes(256), oracle_c.g2_gen_mul(5)):
+        assert oracle_c.lib().oracle_g2_in_subgroup(q, 0) == oracle_c.lib().oracle_g2_in_subgroup(q, 1) == 1
+
+
+def test_golden_fixtures(oracle_c):
+    rows = vectors.load_golden()
+    assert len(rows) >= 30
+    for row in rows:
+        err, out = oracle_c.call(row["Function"], bytes.fromhex(row["Input"]))
+        if "ExpectedErrorCode" in row:
+            assert err == row["ExpectedErrorCode"], row["Name"]
+        else:
+            assert err == 0 and out.hex() == row["Expected"], row["Name"]
+
+
+def test_arithmetic_progression_generator(oracle_c):
+    a, d = oracle_c.g1_gen_mul(5), oracle_c.g1_gen_mul(3)
+    pts = oracle_c.g1_progression(a, d, 6)
+    for i in range(6):
+        assert pts[128 * i:128 * (i + 1)] == oracle_c.g1_gen_mul(5 + 3 * i)
+    pts = oracle_c.g2_progression(oracle_c.g2_gen_mul(2), oracle_c.g2_gen_mul(o.R - 1), 4)   # hits infinity at i = 2
+    for i in range(4):
+        assert pts[256 * i:256 * (i + 1)] == oracle_c.g2_gen_mul((2 - i) % o.R)
