@@ -75,7 +75,7 @@ struct Engine {
   cudaStream_t stream = nullptr;
   std::mutex mu;
   // MSM workspaces
-  Buffer raw, pts, digits, counts, offsets, block_sums, entries, buckets, nodes_a, nodes_b, partial, out, status;
+  Buffer raw, pts, digits, counts, offsets, block_sums, entries, buckets, nodes_a, nodes_b, partial, out, status, order, tasks, task_partials;
   // pairing workspaces
   Buffer pr_raw, pr_offsets, pr_pair_call, pr_call_first, pr_g1, pr_g2, pr_status, pr_f, pr_outs, pr_errs;
   unsigned char* h_out = nullptr;            // pinned: result bytes
@@ -170,8 +170,28 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
   LAUNCH(k_scan_sums, 1, 1024, s, block_sums, nblk);
   LAUNCH(k_scan_fix, nblk, 1024, s, offsets, block_sums, (uint32_t)nbt);
   LAUNCH(k_scatter, blocks_for(n * plan.nwin, 256), 256, s, digits, n, plan, offsets, cursors, entries);
+  // size-ordered bucket schedule + overflow plan for oversized buckets
+  const size_t total_digits = n * plan.nwin;
+  uint32_t cap = (uint32_t)(4 * (total_digits / nbt + 1) + 64);
+  const size_t max_tasks = total_digits / cap + 2;
+  if ((rc = e.order.reserve(nbt * sizeof(uint32_t) + 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters)))) return rc;
+  if ((rc = e.tasks.reserve(max_tasks * (sizeof(OverflowTask) + sizeof(BigBucket))))) return rc;
+  if ((rc = e.task_partials.reserve(max_tasks * sizeof(XYZZ<F>)))) return rc;
+  uint32_t* order = (uint32_t*)e.order.ptr;
+  uint32_t* bin_total = order + nbt;
+  uint32_t* bin_start = bin_total + ORDER_BINS;
+  OrderCounters* oc = (OrderCounters*)(bin_start + ORDER_BINS);
+  OverflowTask* tasks = (OverflowTask*)e.tasks.ptr;
+  BigBucket* big = (BigBucket*)(tasks + max_tasks);
+  XYZZ<F>* task_partials = (XYZZ<F>*)e.task_partials.ptr;
+  CUDA_TRY(cudaMemsetAsync(bin_total, 0, 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters), s));
+  LAUNCH(k_order_hist, nblk, 1024, s, counts, offsets, (uint32_t)nbt, cap, bin_total, oc, big, tasks);
+  LAUNCH(k_order_scan, 1, 1024, s, bin_total, bin_start);
+  LAUNCH(k_order_scatter, nblk, 1024, s, counts, (uint32_t)nbt, bin_start, order);
   g_stage.mark(1, s);
-  LAUNCH(k_accumulate<F>, blocks_for(nbt, 128), 128, s, pts, entries, offsets, counts, (uint32_t)nbt, buckets);
+  LAUNCH(k_accumulate<F>, blocks_for(nbt, 128), 128, s, pts, entries, offsets, counts, order, (uint32_t)nbt, cap, buckets);
+  LAUNCH(k_accumulate_overflow<F>, blocks_for(max_tasks, 128), 128, s, pts, entries, tasks, oc, task_partials);
+  LAUNCH(k_merge_overflow<F>, blocks_for(max_tasks * 32, 128), 128, s, big, oc, task_partials, buckets);
   g_stage.mark(2, s);
   if (g_profile.load()) {   // total sorted entries = non-zero digits D (algorithmic work of k_accumulate)
     uint32_t last_off = 0, last_cnt = 0;
@@ -400,7 +420,10 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   G2Affine* g2 = (G2Affine*)e.pr_g2.ptr;
   int* pstat = (int*)e.pr_status.ptr;
   LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
-  LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, d_offsets, n_calls, g1, g2, pstat, d_outs, d_errs);
+  if ((rc = e.pr_f.reserve(total_pairs * sizeof(Fp12)))) return rc;
+  Fp12* f = (Fp12*)e.pr_f.ptr;
+  LAUNCH(k_pairing_miller, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, f);
+  LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, d_offsets, n_calls, pstat, f, d_outs, d_errs);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
 }
@@ -617,7 +640,7 @@ extern "C" void bls12_b200_shutdown(void) {
     cudaSetDevice(e.device);
     cudaStreamSynchronize(e.stream);
     Buffer* bufs[] = {&e.raw, &e.pts, &e.digits, &e.counts, &e.offsets, &e.block_sums, &e.entries, &e.buckets,
-                      &e.nodes_a, &e.nodes_b, &e.partial, &e.out, &e.status, &e.pr_raw, &e.pr_offsets,
+                      &e.nodes_a, &e.nodes_b, &e.partial, &e.out, &e.status, &e.order, &e.tasks, &e.task_partials, &e.pr_raw, &e.pr_offsets,
                       &e.pr_pair_call, &e.pr_call_first, &e.pr_g1, &e.pr_g2, &e.pr_status, &e.pr_f, &e.pr_outs, &e.pr_errs};
     for (Buffer* b : bufs) b->release();
     cudaFreeHost(e.h_out);

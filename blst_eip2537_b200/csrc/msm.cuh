@@ -182,6 +182,80 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ digits,
   entries[offsets[b] + pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
 }
 
+// ------------------------------------------------------------------------------------------ bucket order
+// Buckets are processed in order of decreasing size so the 32 lanes of a warp walk segments of
+// (nearly) equal length: a counting sort of bucket ids by min(count, ORDER_BINS-1), block-local
+// shared-memory histograms, one global atomic per (block, bin).  The same pass plans the
+// "overflow" work of oversized buckets (skewed / adversarial scalars, e.g. all scalars equal):
+// a bucket thread only ever walks its first `cap` entries; the rest is cut into tasks of <= cap
+// entries, accumulated by other threads and merged by one warp per oversized bucket.
+static constexpr int ORDER_BINS = 1024;
+struct BigBucket { uint32_t bucket, first_task, ntasks, pad; };
+struct OverflowTask { uint32_t bucket, start, len, pad; };
+struct OrderCounters { uint32_t ntasks, nbig; };
+
+__global__ void __launch_bounds__(1024) k_order_hist(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                     uint32_t nbt, uint32_t cap, uint32_t* bin_total, OrderCounters* oc,
+                                                     BigBucket* big, OverflowTask* tasks) {
+  __shared__ uint32_t h[ORDER_BINS];
+  for (int i = threadIdx.x; i < ORDER_BINS; i += 1024) h[i] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * 1024u + threadIdx.x;
+  if (b < nbt) {
+    uint32_t cnt = counts[b];
+    atomicAdd(&h[cnt < ORDER_BINS - 1 ? cnt : ORDER_BINS - 1], 1u);
+    if (cnt > cap) {
+      uint32_t extra = cnt - cap, nt = (extra + cap - 1) / cap;
+      uint32_t first = atomicAdd(&oc->ntasks, nt), slot = atomicAdd(&oc->nbig, 1u);
+      big[slot] = BigBucket{b, first, nt, 0};
+      uint32_t start = offsets[b] + cap;
+      for (uint32_t t = 0; t < nt; t++) {
+        uint32_t len = extra - t * cap < cap ? extra - t * cap : cap;
+        tasks[first + t] = OverflowTask{b, start + t * cap, len, 0};
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ORDER_BINS; i += 1024)
+    if (h[i]) atomicAdd(&bin_total[i], h[i]);
+}
+// bin_start[bin] = number of buckets in strictly larger bins (descending order); one block
+__global__ void __launch_bounds__(1024) k_order_scan(const uint32_t* __restrict__ bin_total, uint32_t* __restrict__ bin_start) {
+  __shared__ uint32_t warp_sums[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int bin = ORDER_BINS - 1 - threadIdx.x;
+  uint32_t v = bin_total[bin], x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = warp_sums[lane], t = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+    warp_sums[lane] = t - s;
+  }
+  __syncthreads();
+  bin_start[bin] = x - v + warp_sums[wid];
+}
+__global__ void __launch_bounds__(1024) k_order_scatter(const uint32_t* __restrict__ counts, uint32_t nbt, uint32_t* bin_cursor,
+                                                        uint32_t* __restrict__ order) {
+  __shared__ uint32_t h[ORDER_BINS], base[ORDER_BINS];
+  for (int i = threadIdx.x; i < ORDER_BINS; i += 1024) h[i] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * 1024u + threadIdx.x, bin = 0, local = 0;
+  if (b < nbt) {
+    uint32_t cnt = counts[b];
+    bin = cnt < ORDER_BINS - 1 ? cnt : ORDER_BINS - 1;
+    local = atomicAdd(&h[bin], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ORDER_BINS; i += 1024)
+    if (h[i]) base[i] = atomicAdd(&bin_cursor[i], h[i]);
+  __syncthreads();
+  if (b < nbt) order[base[bin] + local] = b;
+}
+
 // ------------------------------------------------------------------------------------------ accumulate
 template <class F>
 __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
@@ -194,12 +268,8 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
-                                                    const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
-                                                    uint32_t nbuckets_total, XYZZ<F>* __restrict__ buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets_total) return;
-  uint32_t start = offsets[b], cnt = counts[b];
+__device__ __forceinline__ XYZZ<F> accumulate_segment(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                      uint32_t start, uint32_t cnt) {
   XYZZ<F> acc = xyzz_inf<F>();
   for (uint32_t k = 0; k < cnt; k++) {
     uint32_t e = __ldg(entries + start + k);
@@ -207,7 +277,48 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict_
     if (e >> 31) pt.y = neg(pt.y);
     xyzz_madd(acc, pt);
   }
-  buckets[b] = acc;
+  return acc;
+}
+
+// one thread per bucket, buckets taken in order of decreasing size; at most `cap` entries each
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                    const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                    const uint32_t* __restrict__ order, uint32_t nbuckets_total, uint32_t cap,
+                                                    XYZZ<F>* __restrict__ buckets) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbuckets_total) return;
+  uint32_t b = order[t];
+  uint32_t cnt = counts[b];
+  buckets[b] = accumulate_segment(pts, entries, offsets[b], cnt < cap ? cnt : cap);
+}
+// one thread per overflow task
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate_overflow(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                             const OverflowTask* __restrict__ tasks, const OrderCounters* __restrict__ oc,
+                                                             XYZZ<F>* __restrict__ partials) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= oc->ntasks) return;
+  OverflowTask task = tasks[t];
+  partials[t] = accumulate_segment(pts, entries, task.start, task.len);
+}
+// one warp per oversized bucket: lanes sum strided subsets of its partials, then a shuffle tree
+template <class F>
+__global__ void __launch_bounds__(128) k_merge_overflow(const BigBucket* __restrict__ big, const OrderCounters* __restrict__ oc,
+                                                        const XYZZ<F>* __restrict__ partials, XYZZ<F>* __restrict__ buckets) {
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= oc->nbig) return;
+  BigBucket bb = big[w];
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (uint32_t t = lane; t < bb.ntasks; t += 32) { XYZZ<F> p = partials[bb.first_task + t]; xyzz_add(acc, p); }
+  for (int o = 16; o >= 1; o >>= 1) {
+    XYZZ<F> other;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&other);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&acc);
+    for (int k = 0; k < (int)(sizeof(XYZZ<F>) / 4); k++) dst[k] = __shfl_down_sync(0xffffffffu, src[k], o);
+    if (lane < o) xyzz_add(acc, other);
+  }
+  if (lane == 0) { XYZZ<F> cur = buckets[bb.bucket]; xyzz_add(cur, acc); buckets[bb.bucket] = cur; }
 }
 
 // ------------------------------------------------------------------------------------------ reduce

@@ -282,11 +282,25 @@ __global__ void __launch_bounds__(64) k_pairing_decode(const uint32_t* __restric
   if (code == E_SUCCESS) { g1[j] = p; g2[j] = q; }
 }
 
-// one thread per call: first failing pair decides the error; otherwise product of the
-// pairs' Miller loops, one final exponentiation, is-one -> out[31]
+// one thread per pair: single-pair Miller loop, as the reference runs them (eip2537.c:1060/:1065),
+// result parked in HBM (576 B per pair) for the per-call product
+__global__ void __launch_bounds__(64) k_pairing_miller(const G1Affine* __restrict__ g1, const G2Affine* __restrict__ g2,
+                                                       const int* __restrict__ status, size_t total_pairs, Fp12* __restrict__ f) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total_pairs) return;
+  if (status[j] != E_SUCCESS) return;
+  G1Affine p = g1[j];
+  G2Affine q = g2[j];
+  Fp12 acc;
+  miller_loop(acc, p, q);
+  f[j] = acc;
+}
+
+// one thread per call: first failing pair decides the error; otherwise product of the pairs'
+// Miller values (blst_fp12_mul, :1061), one final exponentiation (:1070), is-one -> out[31] (:1076)
 __global__ void __launch_bounds__(64) k_pairing_calls(const unsigned long long* __restrict__ offsets, size_t n_calls,
-                                                      const G1Affine* __restrict__ g1, const G2Affine* __restrict__ g2,
-                                                      const int* __restrict__ status, uint32_t* __restrict__ outs, int* __restrict__ errs) {
+                                                      const int* __restrict__ status, const Fp12* __restrict__ f,
+                                                      uint32_t* __restrict__ outs, int* __restrict__ errs) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_calls) return;
   size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
@@ -295,12 +309,10 @@ __global__ void __launch_bounds__(64) k_pairing_calls(const unsigned long long* 
   if (first == last) { errs[i] = E_INVALID_LENGTH; return; }
   for (size_t j = first; j < last; j++)
     if (status[j] != E_SUCCESS) { errs[i] = status[j]; return; }
-  Fp12 acc, cur;
-  for (size_t j = first; j < last; j++) {
-    G1Affine p = g1[j];
-    G2Affine q = g2[j];
-    if (j == first) miller_loop(acc, p, q);
-    else { miller_loop(cur, p, q); fp12_mul(acc, acc, cur); }
+  Fp12 acc = f[first], cur;
+  for (size_t j = first + 1; j < last; j++) {
+    cur = f[j];
+    fp12_mul(acc, acc, cur);
   }
   final_exp(acc, acc);
   if (fp12_is_one(acc)) out[7] = 0x01000000u;   // byte 31 of the 32-byte big-endian word
