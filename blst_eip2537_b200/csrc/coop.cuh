@@ -1,0 +1,120 @@
+// coop.cuh -- lane-cooperative point arithmetic for the latency-bound tail of the MSM.
+//
+// The tail of a Pippenger MSM (upper levels of the bucket-reduction tree, the Horner combine of
+// the window sums with its ~240 sequential doublings) has almost no data parallelism; on one
+// thread each point operation is a chain of 9-14 dependent Fp multiplications (~1 us each when a
+// warp runs alone).  Here a group of 8 lanes holds the SAME point in registers; at every
+// dependency level of the formula each lane computes one of the independent products, and the
+// products are exchanged with warp shuffles.  An XYZZ addition becomes 4 multiplication latencies
+// instead of 14, a doubling 3 instead of 9.  Results are bit-identical to ec.cuh's
+// xyzz_add / xyzz_dbl (same formulas, same exceptional-case handling).
+#pragma once
+#include "ec.cuh"
+
+namespace b200 {
+#ifdef __CUDACC__
+
+static constexpr int COOP_LANES = 8;
+
+struct CoopGroup {
+  int lane;        // 0..7 inside the group
+  int base;        // warp lane of the group's lane 0
+  unsigned mask;   // participating warp lanes
+};
+__device__ __forceinline__ CoopGroup coop_group() {
+  CoopGroup g;
+  int wl = threadIdx.x & 31;
+  g.lane = wl & (COOP_LANES - 1);
+  g.base = wl & ~(COOP_LANES - 1);
+  g.mask = 0xFFu << g.base;
+  return g;
+}
+
+template <class F>
+__device__ __forceinline__ F coop_bcast(const F& v, int src, const CoopGroup& g) {
+  F r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_sync(g.mask, s[i], g.base + src);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void coop_pick(F& dst, bool take, const F& v) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = take ? s[i] : d[i];
+}
+
+// 2*p ; every lane of the group passes the same p and receives the same result
+template <class F>
+__device__ __noinline__ void coop_dbl(XYZZ<F>& p, const CoopGroup g) {
+  if (is_inf(p)) return;
+  const int l = g.lane;
+  F u = dbl(p.y);
+  // level 1: v = u^2, x2 = x^2
+  F a = u;
+  coop_pick(a, l == 1, p.x);
+  F r1 = sqr(a);
+  F v = coop_bcast(r1, 0, g), x2 = coop_bcast(r1, 1, g);
+  F m = add(dbl(x2), x2);
+  // level 2: w = u*v, s = x*v, mm = m*m, zz3 = v*zz
+  a = u; F b = v;
+  coop_pick(a, l == 1, p.x);
+  coop_pick(a, l == 2, m); coop_pick(b, l == 2, m);
+  coop_pick(a, l == 3, p.zz);
+  F r2 = mul(a, b);
+  F w = coop_bcast(r2, 0, g), s = coop_bcast(r2, 1, g), mm = coop_bcast(r2, 2, g), zz3 = coop_bcast(r2, 3, g);
+  F x3 = sub(mm, dbl(s));
+  // level 3: ya = m*(s - x3), yb = w*y, zzz3 = w*zzz
+  a = m; b = sub(s, x3);
+  coop_pick(a, l == 1, w); coop_pick(b, l == 1, p.y);
+  coop_pick(a, l == 2, w); coop_pick(b, l == 2, p.zzz);
+  F r3 = mul(a, b);
+  F ya = coop_bcast(r3, 0, g), yb = coop_bcast(r3, 1, g), zzz3 = coop_bcast(r3, 2, g);
+  p.x = x3; p.y = sub(ya, yb); p.zz = zz3; p.zzz = zzz3;
+}
+
+// acc += q ; same contract
+template <class F>
+__device__ __noinline__ void coop_add(XYZZ<F>& acc, const XYZZ<F>& q, const CoopGroup g) {
+  if (is_inf(q)) return;
+  if (is_inf(acc)) { acc = q; return; }
+  const int l = g.lane;
+  // level 1: u1 = X1*ZZ2, u2 = X2*ZZ1, s1 = Y1*ZZZ2, s2 = Y2*ZZZ1, zz12 = ZZ1*ZZ2, zzz12 = ZZZ1*ZZZ2
+  F a = acc.x, b = q.zz;
+  coop_pick(a, l == 1, q.x);     coop_pick(b, l == 1, acc.zz);
+  coop_pick(a, l == 2, acc.y);   coop_pick(b, l == 2, q.zzz);
+  coop_pick(a, l == 3, q.y);     coop_pick(b, l == 3, acc.zzz);
+  coop_pick(a, l == 4, acc.zz);  coop_pick(b, l == 4, q.zz);
+  coop_pick(a, l == 5, acc.zzz); coop_pick(b, l == 5, q.zzz);
+  F r1 = mul(a, b);
+  F u1 = coop_bcast(r1, 0, g), u2 = coop_bcast(r1, 1, g), s1 = coop_bcast(r1, 2, g), s2 = coop_bcast(r1, 3, g);
+  F zz12 = coop_bcast(r1, 4, g), zzz12 = coop_bcast(r1, 5, g);
+  F p = sub(u2, u1), r = sub(s2, s1);
+  if (is_zero(p)) {                       // uniform across the group
+    if (is_zero(r)) coop_dbl(acc, g);     // same point
+    else            acc = xyzz_inf<F>();  // opposite points
+    return;
+  }
+  // level 2: pp = p^2, rr = r^2
+  a = p; coop_pick(a, l == 1, r);
+  F r2 = sqr(a);
+  F pp = coop_bcast(r2, 0, g), rr = coop_bcast(r2, 1, g);
+  // level 3: ppp = p*pp, qq = u1*pp, zz3 = zz12*pp
+  a = p; coop_pick(a, l == 1, u1); coop_pick(a, l == 2, zz12);
+  F r3 = mul(a, pp);
+  F ppp = coop_bcast(r3, 0, g), qq = coop_bcast(r3, 1, g), zz3 = coop_bcast(r3, 2, g);
+  F x3 = sub(sub(rr, ppp), dbl(qq));
+  // level 4: ya = r*(qq - x3), yb = s1*ppp, zzz3 = zzz12*ppp
+  a = r; b = sub(qq, x3);
+  coop_pick(a, l == 1, s1);    coop_pick(b, l == 1, ppp);
+  coop_pick(a, l == 2, zzz12); coop_pick(b, l == 2, ppp);
+  F r4 = mul(a, b);
+  F ya = coop_bcast(r4, 0, g), yb = coop_bcast(r4, 1, g), zzz3 = coop_bcast(r4, 2, g);
+  acc.x = x3; acc.y = sub(ya, yb); acc.zz = zz3; acc.zzz = zzz3;
+}
+
+#endif  // __CUDACC__
+}  // namespace b200

@@ -216,7 +216,7 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
     int remaining_log = plan.log_nb - log_cov;
     int l_log = remaining_log < 3 ? remaining_log : 3;
     size_t out_per_win = nodes_per_win >> l_log;
-    LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win, 128), 128, s, cur,
+    LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win * COOP_LANES, 128), 128, s, cur,
            (uint32_t)(plan.nwin * out_per_win), 1 << l_log, log_cov, nxt);
     Node<F>* t = cur; cur = nxt; nxt = t;
     nodes_per_win = out_per_win;

@@ -349,25 +349,61 @@ B200_HD Fp fp_from_mont(const Fp& a) {
   return mul(a, one);
 }
 
-// a^(p-2); inverse of 0 is 0 (same convention the reference relies on in blst_p1_to_affine)
-B200_HD_NI Fp inv(const Fp& a) {
+// Inverse by the binary extended Euclidean algorithm (~760 shift/subtract steps on 12 limbs, an
+// order of magnitude cheaper than the a^(p-2) ladder of ~480 dependent multiplications).
+// inverse of 0 is 0 (the convention the reference relies on in blst_p1_to_affine).
+// Input/output in Montgomery form: binary_inv(aR) = a^-1 R^-1, then one multiplication by R^3.
+namespace detail {
+B200_HD bool limbs_is_one(const Fp& a) {
+  uint32_t acc = a.v[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < 12; i++) acc |= a.v[i];
+  return acc == 0;
+}
+B200_HD void limbs_shr1(Fp& a, uint32_t top) {
+#pragma unroll
+  for (int i = 0; i < 11; i++) a.v[i] = (a.v[i] >> 1) | (a.v[i + 1] << 31);
+  a.v[11] = (a.v[11] >> 1) | (top << 31);
+}
+// x = x/2 mod p  (x < p)
+B200_HD void halve_mod_p(Fp& x) {
   const uint32_t* p = C_P();
-  // fixed 4-bit window over the public exponent p-2
-  Fp tbl[16];
-  tbl[0] = fp_one();
-  tbl[1] = a;
-  for (int i = 2; i < 16; i++) tbl[i] = mul(tbl[i - 1], a);
-  Fp acc = fp_one();
-  for (int w = 95; w >= 0; w--) {
-    uint32_t word = p[w >> 3];
-    if (w == 0) word -= 2;  // low nibble of p is 0xb, no borrow
-    uint32_t d = (word >> (4 * (w & 7))) & 0xF;
-    if (w != 95) {
-      acc = sqr(acc); acc = sqr(acc); acc = sqr(acc); acc = sqr(acc);
-    }
-    if (d) acc = mul(acc, tbl[d]);
+  uint32_t carry = 0;
+  if (x.v[0] & 1) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { uint64_t s = (uint64_t)x.v[i] + p[i] + c; x.v[i] = (uint32_t)s; c = s >> 32; }
+    carry = (uint32_t)c;
   }
-  return acc;
+  limbs_shr1(x, carry);
+}
+// a >= b as 384-bit integers
+B200_HD bool limbs_geq(const Fp& a, const Fp& b) {
+  uint64_t bw = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - bw; bw = (d >> 32) & 1; }
+  return bw == 0;
+}
+B200_HD void limbs_sub(Fp& a, const Fp& b) {   // a -= b, a >= b
+  uint64_t bw = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - bw; a.v[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+}
+}  // namespace detail
+
+B200_HD_NI Fp inv(const Fp& a) {
+  using namespace detail;
+  if (is_zero(a)) return fp_zero();
+  Fp u = a, v = fp_load_const(C_P()), x1 = fp_zero(), x2 = fp_zero();
+  x1.v[0] = 1;
+  while (!limbs_is_one(u) && !limbs_is_one(v)) {
+    while (!(u.v[0] & 1)) { limbs_shr1(u, 0); halve_mod_p(x1); }
+    while (!(v.v[0] & 1)) { limbs_shr1(v, 0); halve_mod_p(x2); }
+    if (limbs_geq(u, v)) { limbs_sub(u, v); x1 = sub(x1, x2); }
+    else                 { limbs_sub(v, u); x2 = sub(x2, x1); }
+  }
+  Fp r = limbs_is_one(u) ? x1 : x2;
+  return mul(r, fp_load_const(C_R3()));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 // because MULTIEXP inputs are not subgroup-checked.
 #pragma once
 #include "codec.cuh"
+#include "coop.cuh"
 
 namespace b200 {
 
@@ -345,37 +346,41 @@ __global__ void __launch_bounds__(128) k_reduce_leaf(const XYZZ<F>* __restrict__
 }
 // inner level: fold L children, each covering 2^log_m buckets:
 //   s = sum s_t ;  w = sum w_t + 2^log_m * sum_t t*s_t   (t = 0..L-1)
+// These levels have few nodes and long dependency chains, so each node is folded by a group of
+// 8 lanes with the lane-cooperative point operations of coop.cuh.
 template <class F>
 __global__ void __launch_bounds__(128) k_reduce_inner(const Node<F>* __restrict__ in, uint32_t nout_total, int L, int log_m,
                                                       Node<F>* __restrict__ out) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const CoopGroup g = coop_group();
+  uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) / COOP_LANES;
   if (t >= nout_total) return;
   const Node<F>* ch = in + (size_t)t * L;
   XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>(), wsum = xyzz_inf<F>();
   for (int j = L - 1; j >= 0; j--) {
     XYZZ<F> cw = ch[j].w;
-    xyzz_add(wsum, cw);
-    xyzz_add(acc, run);
+    coop_add(wsum, cw, g);
+    coop_add(acc, run, g);
     XYZZ<F> cs = ch[j].s;
-    xyzz_add(run, cs);
+    coop_add(run, cs, g);
   }
-  for (int k = 0; k < log_m; k++) acc = xyzz_dbl(acc);
-  xyzz_add(wsum, acc);
-  out[t].s = run;
-  out[t].w = wsum;
+  for (int k = 0; k < log_m; k++) coop_dbl(acc, g);
+  coop_add(wsum, acc, g);
+  if (g.lane == 0) { out[t].s = run; out[t].w = wsum; }
 }
 
-// window totals T_w = roots[w].w ; result = sum_w 2^(c*w) T_w  (Horner from the top window)
+// window totals T_w = roots[w].w ; result = sum_w 2^(c*w) T_w  (Horner from the top window);
+// one group of 8 cooperating lanes walks the ~240 sequential doublings
 template <class F>
 __global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan, XYZZ<F>* __restrict__ out_partial) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= COOP_LANES) return;
+  const CoopGroup g = coop_group();
   XYZZ<F> acc = roots[plan.nwin - 1].w;
   for (int w = plan.nwin - 2; w >= 0; w--) {
-    for (int k = 0; k < plan.c; k++) acc = xyzz_dbl(acc);
+    for (int k = 0; k < plan.c; k++) coop_dbl(acc, g);
     XYZZ<F> t = roots[w].w;
-    xyzz_add(acc, t);
+    coop_add(acc, t, g);
   }
-  *out_partial = acc;
+  if (g.lane == 0) *out_partial = acc;
 }
 
 // sum `count` partial results (multi-GPU gather, or count = 1), convert to affine, encode
