@@ -526,21 +526,23 @@ __global__ void __launch_bounds__(256) k_fp_chain(int iters, Fp* out) {
   if (threadIdx.x == 0) out[blockIdx.x] = x;
   else if (x.v[0] == 0xdeadbeefu && x.v[5] == 0x12345u) out[blockIdx.x] = x;
 }
-// 8 independent 64-bit accumulators per thread, each acc += a*b (IMAD.WIDE.U32): raw pipe peak
+// raw integer-multiply pipe probe: 16 independent 64-bit accumulators per thread, each
+// acc = a*b + acc (mad.wide.u32 -> IMAD.WIDE.U32), nothing else in the loop body
 __global__ void __launch_bounds__(256) k_imad_peak(int iters, unsigned long long* out) {
   unsigned a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7;
-  unsigned long long c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+  unsigned long long c[16];
+#pragma unroll
+  for (int u = 0; u < 16; u++) c[u] = u + 1;
   for (int k = 0; k < iters; k++) {
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      c0 += (unsigned long long)a * b; c1 += (unsigned long long)a * (b + 1);
-      c2 += (unsigned long long)(a + 1) * b; c3 += (unsigned long long)(a + 2) * b;
-      c4 += (unsigned long long)a * (b + 3); c5 += (unsigned long long)(a + 3) * b;
-      c6 += (unsigned long long)a * (b + 5); c7 += (unsigned long long)(a + 5) * b;
-      a += (unsigned)c0; b ^= (unsigned)(c7 >> 32);
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[u]) : "r"(a), "r"(b));
     }
   }
-  unsigned long long r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  unsigned long long r = 0;
+#pragma unroll
+  for (int u = 0; u < 16; u++) r ^= c[u];
   if (r == 0x123456789ull || threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
