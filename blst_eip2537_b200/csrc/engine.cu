@@ -546,6 +546,31 @@ __global__ void __launch_bounds__(256) k_imad_peak(int iters, unsigned long long
   if (r == 0x123456789ull || threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
+// carry-chain probe: 4 independent 13-word accumulators, each fed by mad.lo.cc/madc.hi.cc rows
+// (the IMAD.WIDE.U32.X form the Montgomery multiply uses): 24 MAC32 per iteration per thread
+__global__ void __launch_bounds__(256) k_imad_carry_probe(int iters, unsigned long long* out) {
+  uint32_t a[12], acc[4][13];
+#pragma unroll
+  for (int i = 0; i < 12; i++) a[i] = threadIdx.x * 2654435761u + i;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int i = 0; i < 13; i++) acc[k][i] = k + i;
+  uint32_t b = blockIdx.x * 40503u + 7;
+#ifdef __CUDA_ARCH__
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) b200::detail::mad_row(acc[k], a, b);
+  }
+#endif
+  unsigned long long r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int i = 0; i < 13; i++) r += acc[k][i];
+  if (r == 0x123456789ull || threadIdx.x == 0) out[blockIdx.x] = r;
+}
+
 extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48) {
   Engine* ep;
   int rc = engine_get(&ep, -1);
@@ -560,8 +585,9 @@ extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, in
   cudaStream_t s = e.stream;
   for (int rep = 0; rep < 2; rep++) {   // first pass warms up
     CUDA_TRY2(cudaEventRecord(t0, s));
-    if (mode == 0) LAUNCH(k_fp_chain, nblk, 256, s, iters, (Fp*)e.pts.ptr);
-    else           LAUNCH(k_imad_peak, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
+    if (mode == 0)      LAUNCH(k_fp_chain, nblk, 256, s, iters, (Fp*)e.pts.ptr);
+    else if (mode == 1) LAUNCH(k_imad_peak, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
+    else                LAUNCH(k_imad_carry_probe, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
     CUDA_TRY2(cudaEventRecord(t1, s));
     CUDA_TRY2(cudaStreamSynchronize(s));
   }
