@@ -527,22 +527,46 @@ __global__ void __launch_bounds__(256) k_fp_chain(int iters, Fp* out) {
   else if (x.v[0] == 0xdeadbeefu && x.v[5] == 0x12345u) out[blockIdx.x] = x;
 }
 // raw integer-multiply pipe probe: 16 independent 64-bit accumulators per thread, each
-// acc = a*b + acc (mad.wide.u32 -> IMAD.WIDE.U32), nothing else in the loop body
+// acc = a*b + acc (mad.wide.u32 -> IMAD.WIDE.U32).  The multiplier changes every pass (xor with an
+// accumulator word), otherwise ptxas hoists the loop-invariant products and the loop degenerates into
+// 64-bit adds (an earlier version of this probe did exactly that and over-reported the peak 2x).
 __global__ void __launch_bounds__(256) k_imad_peak(int iters, unsigned long long* out) {
-  unsigned a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7;
+  unsigned a[16], b = blockIdx.x * 40503u + 7;
   unsigned long long c[16];
 #pragma unroll
-  for (int u = 0; u < 16; u++) c[u] = u + 1;
+  for (int u = 0; u < 16; u++) { c[u] = u + 1; a[u] = threadIdx.x * 2654435761u + 977u * u; }
   for (int k = 0; k < iters; k++) {
 #pragma unroll
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-      for (int u = 0; u < 16; u++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[u]) : "r"(a), "r"(b));
+      for (int u = 0; u < 16; u++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[u]) : "r"(a[u]), "r"(b));
+      b ^= (unsigned)c[r];
     }
   }
   unsigned long long r = 0;
 #pragma unroll
   for (int u = 0; u < 16; u++) r ^= c[u];
+  if (r == 0x123456789ull || threadIdx.x == 0) out[blockIdx.x] = r;
+}
+// same with separate 32-bit halves: lo = a*b + lo (IMAD), hi = mulhi(a,b) + hi (IMAD.HI), no carry between them
+__global__ void __launch_bounds__(256) k_imad32_peak(int iters, unsigned long long* out) {
+  unsigned a[16], b = blockIdx.x * 40503u + 7, lo[16], hi[16];
+#pragma unroll
+  for (int u = 0; u < 16; u++) { lo[u] = u + 1; hi[u] = 3 * u; a[u] = threadIdx.x * 2654435761u + 977u * u; }
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[u]) : "r"(a[u]), "r"(b));
+        asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[u]) : "r"(a[u]), "r"(b));
+      }
+      b ^= lo[r];
+    }
+  }
+  unsigned long long r = 0;
+#pragma unroll
+  for (int u = 0; u < 16; u++) r ^= lo[u] + ((unsigned long long)hi[u] << 32);
   if (r == 0x123456789ull || threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
@@ -587,7 +611,8 @@ extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, in
     CUDA_TRY2(cudaEventRecord(t0, s));
     if (mode == 0)      LAUNCH(k_fp_chain, nblk, 256, s, iters, (Fp*)e.pts.ptr);
     else if (mode == 1) LAUNCH(k_imad_peak, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
-    else                LAUNCH(k_imad_carry_probe, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
+    else if (mode == 2) LAUNCH(k_imad_carry_probe, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
+    else                LAUNCH(k_imad32_peak, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
     CUDA_TRY2(cudaEventRecord(t1, s));
     CUDA_TRY2(cudaStreamSynchronize(s));
   }
@@ -680,6 +705,7 @@ extern "C" void bls12_b200_shutdown(void) {
 extern "C" const char* bls12_b200_last_error(void) { return g_last_error; }
 extern "C" uint64_t bls12_b200_launch_count(void) { return g_launches.load(); }
 extern "C" void bls12_b200_set_window(int c) { g_forced_window.store(c); }
+extern "C" size_t bls12_b200_partial_bytes(int group) { return group == 1 ? sizeof(XYZZ<Fp>) : sizeof(XYZZ<Fp2>); }
 extern "C" void bls12_b200_set_profile(int on) { g_profile.store(on); }
 // stage_ms[4] = {decode+digits+sort, accumulate, bucket reduce tree, window combine} of the last profiled MSM
 extern "C" EIP2537_ERROR bls12_b200_last_msm_profile(float* stage_ms4, uint64_t* nonzero_digits) {

@@ -32,7 +32,7 @@ class CudaBackend:
         from . import _native
         self.L = _native.lib()
         self.group = group
-        self.xy = 192 if group == 1 else 384
+        self.xy = int(self.L.bls12_b200_partial_bytes(group))
         self.plen = 128 if group == 1 else 256
         self.device = torch.device("cuda", torch.cuda.current_device())
 

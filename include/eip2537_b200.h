@@ -44,7 +44,9 @@ EIP2537_ERROR bls12_pairing_batch(byte* outs, EIP2537_ERROR* errs, const byte* i
  *  Asynchronous on `stream`; the caller synchronises and reads d_status / d_out. */
 EIP2537_ERROR bls12_b200_msm_device(int group, const void* d_in, size_t n, void* d_out,
                                     uint64_t* d_status, void* stream);
-/* partial sum only (multi-GPU sharding): XYZZ coordinates, Montgomery limbs, 192 / 384 bytes.
+/* size in bytes of one partial sum (XYZZ coordinates, Montgomery limbs) for group 1 / 2 */
+size_t bls12_b200_partial_bytes(int group);
+/* partial sum only (multi-GPU sharding): bls12_b200_partial_bytes(group) bytes at d_partial.
  * index_base is added to pair indices reported in d_status (global index of this shard). */
 EIP2537_ERROR bls12_b200_msm_partial_device(int group, const void* d_in, size_t n, uint64_t index_base,
                                             void* d_partial, uint64_t* d_status, void* stream);
@@ -62,8 +64,10 @@ EIP2537_ERROR bls12_b200_pairing_batch_device(const void* d_in, const uint64_t* 
 EIP2537_ERROR bls12_b200_g1_generator_mul(byte* out, const byte* scalars, size_t n);
 EIP2537_ERROR bls12_b200_g2_generator_mul(byte* out, const byte* scalars, size_t n);
 
-/* ---- K1 microbenchmarks: n_threads chains of `iters` dependent Fp multiplications; returns
- *      elapsed milliseconds in *ms (CUDA events).  mode 0 = Fp mul, 1 = raw IMAD.WIDE peak probe */
+/* ---- K1 microbenchmarks over n_threads threads x `iters` iterations; elapsed milliseconds in *ms
+ *      (CUDA events).  mode 0 = dependent Fp multiplications (digest = thread 0's result),
+ *      1 = IMAD.WIDE.U32 issue-rate probe (64 MAC32 per iteration), 2 = carry-chained
+ *      IMAD.WIDE.U32.X probe (24 MAC32 per iteration), 3 = IMAD + IMAD.HI pairs (64 MAC32 per iteration) */
 EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48);
 
 /* ---- per-stage timing of the MSM pipeline (CUDA events on the launching stream), for the

@@ -18,7 +18,7 @@ what = sys.argv[1:] or ["micro", "msm", "pairing"]
 
 if "micro" in what:
     nthr = 148 * 2048
-    for mode, name, per in ((1, "imad.wide", 64), (2, "imad.wide carry chains", 24), (0, "fp_mul", 1)):
+    for mode, name, per in ((1, "imad.wide (operands vary)", 64), (3, "imad lo+hi pairs", 64), (2, "imad.wide carry chains", 24), (0, "fp_mul", 1)):
         iters = 2000 if mode == 1 else 1000
         L.bls12_b200_fp_microbench(mode, nthr, iters, ctypes.byref(ms), None)
         ops = nthr * iters * per
