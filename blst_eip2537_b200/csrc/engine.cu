@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -73,6 +74,9 @@ struct Engine {
   int device = -1;
   bool ready = false;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // latency-bound MSM tail, overlapped with accumulation
+  cudaEvent_t ev_group[8] = {};
+  cudaEvent_t ev_tail = nullptr;
   std::mutex mu;
   // MSM workspaces
   Buffer raw, pts, digits, counts, offsets, block_sums, entries, buckets, nodes_a, nodes_b, partial, out, status, order, tasks, task_partials;
@@ -97,6 +101,14 @@ static int engine_get(Engine** out, int device) {
       CUDA_TRY(cudaGetDevice(&prev));
       CUDA_TRY(cudaSetDevice(device));
       CUDA_TRY(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+      {
+        // highest priority: the tail's few blocks must get SM slots as accumulate blocks retire
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&e.stream2, cudaStreamNonBlocking, hi));
+      }
+      for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreateWithFlags(&e.ev_group[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming));
       CUDA_TRY(cudaMallocHost((void**)&e.h_out, 4096));
       CUDA_TRY(cudaMallocHost((void**)&e.h_status, 64));
       CUDA_TRY(cudaSetDevice(prev));
@@ -170,61 +182,89 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
   LAUNCH(k_scan_sums, 1, 1024, s, block_sums, nblk);
   LAUNCH(k_scan_fix, nblk, 1024, s, offsets, block_sums, (uint32_t)nbt);
   LAUNCH(k_scatter, blocks_for(n * plan.nwin, 256), 256, s, digits, n, plan, offsets, cursors, entries);
-  // size-ordered bucket schedule + overflow plan for oversized buckets
+  // ---- windows are processed in groups, top group first.  Stage A of a group (size-ordered
+  // schedule + bucket accumulation: throughput-bound, fills the GPU) runs on the caller's stream;
+  // stage B (bucket-reduction tree + Horner step: latency-bound, a few hundred threads) runs on a
+  // second stream, so the tail of group g hides behind the accumulation of group g+1.
   const size_t total_digits = n * plan.nwin;
   uint32_t cap = (uint32_t)(4 * (total_digits / nbt + 1) + 64);
-  const size_t max_tasks = total_digits / cap + 2;
-  if ((rc = e.order.reserve(nbt * sizeof(uint32_t) + 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters)))) return rc;
+  // Measured on B200 (2^20 G1: 10.7 ms sequential vs 11.7 ms overlapped, G2 2^18: 14.6 vs 23.3): the
+  // tail's dependent chains need the multiply pipe to themselves, and co-resident accumulate warps
+  // stretch them by more than the overlap hides.  The grouped path is kept (B200_MSM_PIPELINE=1)
+  // for experiments; the default is one group on one stream.
+  static const bool want_pipeline = getenv("B200_MSM_PIPELINE") != nullptr;
+  const bool pipelined = want_pipeline && !g_profile.load() && plan.nwin >= 8;
+  const int gw = pipelined ? (plan.nwin + 3) / 4 : plan.nwin;      // windows per group
+  const int ngroups = (plan.nwin + gw - 1) / gw;
+  cudaStream_t t = pipelined ? e.stream2 : s;
+  const size_t max_tasks = (n * (size_t)gw) / cap + 2;
+  const size_t gb_max = (size_t)gw * plan.nb;                        // buckets per group (upper bound)
+  if ((rc = e.order.reserve(gb_max * sizeof(uint32_t) + 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters)))) return rc;
   if ((rc = e.tasks.reserve(max_tasks * (sizeof(OverflowTask) + sizeof(BigBucket))))) return rc;
   if ((rc = e.task_partials.reserve(max_tasks * sizeof(XYZZ<F>)))) return rc;
+  int L0_log = plan.log_nb < 4 ? plan.log_nb : 4;
+  const size_t leaf_nodes_per_win = plan.nb >> L0_log;
+  if ((rc = e.nodes_a.reserve((size_t)gw * leaf_nodes_per_win * sizeof(Node<F>)))) return rc;
+  if ((rc = e.nodes_b.reserve((size_t)gw * (leaf_nodes_per_win / 2 + 1) * sizeof(Node<F>)))) return rc;
   uint32_t* order = (uint32_t*)e.order.ptr;
-  uint32_t* bin_total = order + nbt;
+  uint32_t* bin_total = order + gb_max;
   uint32_t* bin_start = bin_total + ORDER_BINS;
   OrderCounters* oc = (OrderCounters*)(bin_start + ORDER_BINS);
   OverflowTask* tasks = (OverflowTask*)e.tasks.ptr;
   BigBucket* big = (BigBucket*)(tasks + max_tasks);
   XYZZ<F>* task_partials = (XYZZ<F>*)e.task_partials.ptr;
-  CUDA_TRY(cudaMemsetAsync(bin_total, 0, 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters), s));
-  LAUNCH(k_order_hist, nblk, 1024, s, counts, offsets, (uint32_t)nbt, cap, bin_total, oc, big, tasks);
-  LAUNCH(k_order_scan, 1, 1024, s, bin_total, bin_start);
-  LAUNCH(k_order_scatter, nblk, 1024, s, counts, (uint32_t)nbt, bin_start, order);
-  g_stage.mark(1, s);
-  LAUNCH(k_accumulate<F>, blocks_for(nbt, 128), 128, s, pts, entries, offsets, counts, order, (uint32_t)nbt, cap, buckets);
-  LAUNCH(k_accumulate_overflow<F>, blocks_for(max_tasks, 128), 128, s, pts, entries, tasks, oc, task_partials);
-  LAUNCH(k_merge_overflow<F>, blocks_for(max_tasks * 32, 128), 128, s, big, oc, task_partials, buckets);
-  g_stage.mark(2, s);
-  if (g_profile.load()) {   // total sorted entries = non-zero digits D (algorithmic work of k_accumulate)
-    uint32_t last_off = 0, last_cnt = 0;
-    cudaMemcpyAsync(&last_off, offsets + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(&last_cnt, counts + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
-    g_last_entries = (unsigned long long)last_off + last_cnt;
-  }
 
-  // reduction tree: leaf folds L0 buckets, inner levels fold L children
-  int log_cov = 0;                       // log2(buckets covered per node)
-  int L0_log = plan.log_nb < 4 ? plan.log_nb : 4;
-  size_t nodes_per_win = plan.nb >> L0_log;
-  if ((rc = e.nodes_a.reserve((size_t)plan.nwin * nodes_per_win * sizeof(Node<F>)))) return rc;
-  if ((rc = e.nodes_b.reserve((size_t)plan.nwin * (nodes_per_win / 2 + 1) * sizeof(Node<F>)))) return rc;
-  Node<F>* cur = (Node<F>*)e.nodes_a.ptr;
-  Node<F>* nxt = (Node<F>*)e.nodes_b.ptr;
-  LAUNCH(k_reduce_leaf<F>, blocks_for(plan.nwin * nodes_per_win, 128), 128, s, buckets,
-         (uint32_t)(plan.nwin * nodes_per_win), 1 << L0_log, cur);
-  log_cov = L0_log;
-  while (nodes_per_win > 1) {
-    int remaining_log = plan.log_nb - log_cov;
-    int l_log = remaining_log < 3 ? remaining_log : 3;
-    size_t out_per_win = nodes_per_win >> l_log;
-    LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win * COOP_LANES, 128), 128, s, cur,
-           (uint32_t)(plan.nwin * out_per_win), 1 << l_log, log_cov, nxt);
-    Node<F>* t = cur; cur = nxt; nxt = t;
-    nodes_per_win = out_per_win;
-    log_cov += l_log;
+  g_stage.mark(1, s);
+  for (int g = 0; g < ngroups; g++) {
+    const int w1 = plan.nwin - g * gw, w0 = w1 - gw < 0 ? 0 : w1 - gw;   // windows [w0, w1), top group first
+    const int nw = w1 - w0;
+    const size_t b0 = (size_t)w0 * plan.nb, gb = (size_t)nw * plan.nb;
+    const unsigned gblk = blocks_for(gb, 1024);
+    // ---- stage A
+    CUDA_TRY(cudaMemsetAsync(bin_total, 0, 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters), s));
+    LAUNCH(k_order_hist, gblk, 1024, s, counts + b0, offsets + b0, (uint32_t)gb, cap, bin_total, oc, big, tasks);
+    LAUNCH(k_order_scan, 1, 1024, s, bin_total, bin_start);
+    LAUNCH(k_order_scatter, gblk, 1024, s, counts + b0, (uint32_t)gb, bin_start, order);
+    LAUNCH(k_accumulate<F>, blocks_for(gb, 128), 128, s, pts, entries, offsets + b0, counts + b0, order, (uint32_t)gb, cap, buckets + b0);
+    LAUNCH(k_accumulate_overflow<F>, blocks_for(max_tasks, 128), 128, s, pts, entries, tasks, oc, task_partials);
+    LAUNCH(k_merge_overflow<F>, blocks_for(max_tasks * 32, 128), 128, s, big, oc, task_partials, buckets + b0);
+    if (pipelined) {
+      CUDA_TRY(cudaEventRecord(e.ev_group[g], s));
+      CUDA_TRY(cudaStreamWaitEvent(t, e.ev_group[g], 0));
+    } else if (g == ngroups - 1) {
+      g_stage.mark(2, s);
+      if (g_profile.load()) {   // total sorted entries = non-zero digits D (algorithmic work of k_accumulate)
+        uint32_t last_off = 0, last_cnt = 0;
+        cudaMemcpyAsync(&last_off, offsets + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(&last_cnt, counts + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        g_last_entries = (unsigned long long)last_off + last_cnt;
+      }
+    }
+    // ---- stage B: reduction tree (leaf folds 2^L0_log buckets, inner levels fold up to 8 children)
+    Node<F>* cur = (Node<F>*)e.nodes_a.ptr;
+    Node<F>* nxt = (Node<F>*)e.nodes_b.ptr;
+    size_t nodes_per_win = leaf_nodes_per_win;
+    LAUNCH(k_reduce_leaf<F>, blocks_for(nw * nodes_per_win, 128), 128, t, buckets + b0, (uint32_t)(nw * nodes_per_win), 1 << L0_log, cur);
+    int log_cov = L0_log;                  // log2(buckets covered per node)
+    while (nodes_per_win > 1) {
+      int remaining_log = plan.log_nb - log_cov;
+      int l_log = remaining_log < 3 ? remaining_log : 3;
+      size_t out_per_win = nodes_per_win >> l_log;
+      LAUNCH(k_reduce_inner<F>, blocks_for(nw * out_per_win * COOP_LANES, 128), 128, t, cur, (uint32_t)(nw * out_per_win), 1 << l_log, log_cov, nxt);
+      Node<F>* tmp = cur; cur = nxt; nxt = tmp;
+      nodes_per_win = out_per_win;
+      log_cov += l_log;
+    }
+    if (!pipelined && g == ngroups - 1) g_stage.mark(3, s);
+    LAUNCH(k_window_combine<F>, 1, 32, t, cur, nw, plan.c, g == 0 ? 1 : 0, d_partial);
   }
-  g_stage.mark(3, s);
-  LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan, d_partial);
-  g_stage.mark(4, s);
+  if (pipelined) {
+    CUDA_TRY(cudaEventRecord(e.ev_tail, t));
+    CUDA_TRY(cudaStreamWaitEvent(s, e.ev_tail, 0));
+  } else {
+    g_stage.mark(4, s);
+  }
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
 }
@@ -699,6 +739,9 @@ extern "C" void bls12_b200_shutdown(void) {
     cudaFreeHost(e.h_out);
     cudaFreeHost(e.h_status);
     cudaStreamDestroy(e.stream);
+    cudaStreamDestroy(e.stream2);
+    for (int k = 0; k < 8; k++) cudaEventDestroy(e.ev_group[k]);
+    cudaEventDestroy(e.ev_tail);
     e.ready = false;
   }
 }

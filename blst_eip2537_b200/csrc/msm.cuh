@@ -368,19 +368,20 @@ __global__ void __launch_bounds__(128) k_reduce_inner(const Node<F>* __restrict_
   if (g.lane == 0) { out[t].s = run; out[t].w = wsum; }
 }
 
-// window totals T_w = roots[w].w ; result = sum_w 2^(c*w) T_w  (Horner from the top window);
-// one group of 8 cooperating lanes walks the ~240 sequential doublings
+// Horner step over one group of windows (top group first): acc = 2^c * acc + T_w for the group's
+// windows from the top down, T_w = roots[w].w.  One group of 8 cooperating lanes walks the
+// sequential doublings (~240 in total over all groups).
 template <class F>
-__global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan, XYZZ<F>* __restrict__ out_partial) {
+__global__ void k_window_combine(const Node<F>* __restrict__ roots, int nw, int c, int first, XYZZ<F>* __restrict__ acc_io) {
   if (blockIdx.x != 0 || threadIdx.x >= COOP_LANES) return;
   const CoopGroup g = coop_group();
-  XYZZ<F> acc = roots[plan.nwin - 1].w;
-  for (int w = plan.nwin - 2; w >= 0; w--) {
-    for (int k = 0; k < plan.c; k++) coop_dbl(acc, g);
+  XYZZ<F> acc = first ? xyzz_inf<F>() : *acc_io;
+  for (int w = nw - 1; w >= 0; w--) {
+    for (int k = 0; k < c; k++) coop_dbl(acc, g);
     XYZZ<F> t = roots[w].w;
     coop_add(acc, t, g);
   }
-  if (g.lane == 0) *out_partial = acc;
+  if (g.lane == 0) *acc_io = acc;
 }
 
 // sum `count` partial results (multi-GPU gather, or count = 1), convert to affine, encode
