@@ -74,7 +74,7 @@ struct Engine {
   int device = -1;
   bool ready = false;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;            // latency-bound MSM tail, overlapped with accumulation
+  cudaStream_t stream2 = nullptr;            // H2D copies of streamed MSM chunks (overlap with accumulation)
   cudaEvent_t ev_group[8] = {};
   cudaEvent_t ev_tail = nullptr;
   std::mutex mu;
@@ -150,125 +150,145 @@ struct StageTimer {
 static StageTimer g_stage;
 static unsigned long long g_last_entries = 0;
 
+// The MSM runs in three phases so that a host-resident input can be STREAMED: bucket accumulation is
+// additive, so each chunk of pairs is decoded, sorted and accumulated on top of the buckets left by
+// the previous chunks while the next chunk is still crossing PCIe; the latency-bound tail (bucket
+// reduction, window combine) runs once at the end.
 template <class F>
-static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t index_base, XYZZ<F>* d_partial,
-                        unsigned long long* d_status, cudaStream_t s) {
-  MsmPlan plan = make_plan(choose_window(n));
-  const size_t nbt = (size_t)plan.nwin * plan.nb;   // total buckets, uniform layout
+struct MsmRun {
+  MsmPlan plan;
+  size_t nbt, chunk_cap;
+  Affine<F>* pts; int* digits; uint32_t *counts, *cursors, *offsets, *block_sums, *entries, *order, *bin_total, *bin_start;
+  OrderCounters* oc; OverflowTask* tasks; BigBucket* big; XYZZ<F>* task_partials; XYZZ<F>* buckets;
+  size_t max_tasks;
+};
+
+template <class F>
+static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
+  r.plan = make_plan(choose_window(n_total));
+  const MsmPlan& plan = r.plan;
+  r.nbt = (size_t)plan.nwin * plan.nb;   // total buckets, uniform layout
+  r.chunk_cap = chunk_n;
+  const size_t nbt = r.nbt;
   int rc;
-  if ((rc = e.pts.reserve(n * sizeof(Affine<F>)))) return rc;
-  if ((rc = e.digits.reserve(n * plan.nwin * sizeof(int)))) return rc;
+  if ((rc = e.pts.reserve(chunk_n * sizeof(Affine<F>)))) return rc;
+  if ((rc = e.digits.reserve(chunk_n * plan.nwin * sizeof(int)))) return rc;
   if ((rc = e.counts.reserve(2 * nbt * sizeof(uint32_t)))) return rc;       // counts + cursors
   if ((rc = e.offsets.reserve(nbt * sizeof(uint32_t)))) return rc;
   if ((rc = e.block_sums.reserve((nbt / 1024 + 2) * sizeof(uint32_t)))) return rc;
-  if ((rc = e.entries.reserve(n * plan.nwin * sizeof(uint32_t)))) return rc;
+  if ((rc = e.entries.reserve(chunk_n * plan.nwin * sizeof(uint32_t)))) return rc;
   if ((rc = e.buckets.reserve(nbt * sizeof(XYZZ<F>)))) return rc;
+  r.max_tasks = (chunk_n * (size_t)plan.nwin) / 64 + 2;      // cap >= 64 entries per task
+  if ((rc = e.order.reserve(nbt * sizeof(uint32_t) + 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters)))) return rc;
+  if ((rc = e.tasks.reserve(r.max_tasks * (sizeof(OverflowTask) + sizeof(BigBucket))))) return rc;
+  if ((rc = e.task_partials.reserve(r.max_tasks * sizeof(XYZZ<F>)))) return rc;
+  r.pts = (Affine<F>*)e.pts.ptr;
+  r.digits = (int*)e.digits.ptr;
+  r.counts = (uint32_t*)e.counts.ptr;
+  r.cursors = r.counts + nbt;
+  r.offsets = (uint32_t*)e.offsets.ptr;
+  r.block_sums = (uint32_t*)e.block_sums.ptr;
+  r.entries = (uint32_t*)e.entries.ptr;
+  r.buckets = (XYZZ<F>*)e.buckets.ptr;
+  r.order = (uint32_t*)e.order.ptr;
+  r.bin_total = r.order + nbt;
+  r.bin_start = r.bin_total + ORDER_BINS;
+  r.oc = (OrderCounters*)(r.bin_start + ORDER_BINS);
+  r.tasks = (OverflowTask*)e.tasks.ptr;
+  r.big = (BigBucket*)(r.tasks + r.max_tasks);
+  r.task_partials = (XYZZ<F>*)e.task_partials.ptr;
+  return E_SUCCESS;
+}
 
-  Affine<F>* pts = (Affine<F>*)e.pts.ptr;
-  int* digits = (int*)e.digits.ptr;
-  uint32_t* counts = (uint32_t*)e.counts.ptr;
-  uint32_t* cursors = counts + nbt;
-  uint32_t* offsets = (uint32_t*)e.offsets.ptr;
-  uint32_t* block_sums = (uint32_t*)e.block_sums.ptr;
-  uint32_t* entries = (uint32_t*)e.entries.ptr;
-  XYZZ<F>* buckets = (XYZZ<F>*)e.buckets.ptr;
-
-  g_stage.mark(0, s);
-  CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * nbt * sizeof(uint32_t), s));
-  LAUNCH(k_decode<F>, blocks_for(n, 128), 128, s, d_raw, n, pts, d_status, (size_t)index_base);
-  LAUNCH(k_digits<F>, blocks_for(n, 256), 256, s, d_raw, n, pts, plan, digits, counts);
+// decode + digit recoding + counting sort + size-ordered bucket accumulation of one chunk of pairs
+template <class F>
+static int msm_feed(Engine& e, MsmRun<F>& r, const uint32_t* d_raw, size_t n, uint64_t index_base, bool first,
+                    unsigned long long* d_status, cudaStream_t s) {
+  (void)e;
+  const MsmPlan& plan = r.plan;
+  const size_t nbt = r.nbt;
+  if (first) g_stage.mark(0, s);
+  CUDA_TRY(cudaMemsetAsync(r.counts, 0, 2 * nbt * sizeof(uint32_t), s));
+  LAUNCH(k_decode<F>, blocks_for(n, 128), 128, s, d_raw, n, r.pts, d_status, (size_t)index_base);
+  LAUNCH(k_digits<F>, blocks_for(n, 256), 256, s, d_raw, n, r.pts, plan, r.digits, r.counts);
   unsigned nblk = blocks_for(nbt, 1024);
-  LAUNCH(k_scan_blocks, nblk, 1024, s, counts, offsets, block_sums, (uint32_t)nbt);
-  LAUNCH(k_scan_sums, 1, 1024, s, block_sums, nblk);
-  LAUNCH(k_scan_fix, nblk, 1024, s, offsets, block_sums, (uint32_t)nbt);
-  LAUNCH(k_scatter, blocks_for(n * plan.nwin, 256), 256, s, digits, n, plan, offsets, cursors, entries);
-  // ---- windows are processed in groups, top group first.  Stage A of a group (size-ordered
-  // schedule + bucket accumulation: throughput-bound, fills the GPU) runs on the caller's stream;
-  // stage B (bucket-reduction tree + Horner step: latency-bound, a few hundred threads) runs on a
-  // second stream, so the tail of group g hides behind the accumulation of group g+1.
+  LAUNCH(k_scan_blocks, nblk, 1024, s, r.counts, r.offsets, r.block_sums, (uint32_t)nbt);
+  LAUNCH(k_scan_sums, 1, 1024, s, r.block_sums, nblk);
+  LAUNCH(k_scan_fix, nblk, 1024, s, r.offsets, r.block_sums, (uint32_t)nbt);
+  LAUNCH(k_scatter, blocks_for(n * plan.nwin, 256), 256, s, r.digits, n, plan, r.offsets, r.cursors, r.entries);
+  // size-ordered bucket schedule + overflow plan for oversized buckets
   const size_t total_digits = n * plan.nwin;
   uint32_t cap = (uint32_t)(4 * (total_digits / nbt + 1) + 64);
-  // Measured on B200 (2^20 G1: 10.7 ms sequential vs 11.7 ms overlapped, G2 2^18: 14.6 vs 23.3): the
-  // tail's dependent chains need the multiply pipe to themselves, and co-resident accumulate warps
-  // stretch them by more than the overlap hides.  The grouped path is kept (B200_MSM_PIPELINE=1)
-  // for experiments; the default is one group on one stream.
-  static const bool want_pipeline = getenv("B200_MSM_PIPELINE") != nullptr;
-  const bool pipelined = want_pipeline && !g_profile.load() && plan.nwin >= 8;
-  const int gw = pipelined ? (plan.nwin + 3) / 4 : plan.nwin;      // windows per group
-  const int ngroups = (plan.nwin + gw - 1) / gw;
-  cudaStream_t t = pipelined ? e.stream2 : s;
-  const size_t max_tasks = (n * (size_t)gw) / cap + 2;
-  const size_t gb_max = (size_t)gw * plan.nb;                        // buckets per group (upper bound)
-  if ((rc = e.order.reserve(gb_max * sizeof(uint32_t) + 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters)))) return rc;
-  if ((rc = e.tasks.reserve(max_tasks * (sizeof(OverflowTask) + sizeof(BigBucket))))) return rc;
-  if ((rc = e.task_partials.reserve(max_tasks * sizeof(XYZZ<F>)))) return rc;
-  int L0_log = plan.log_nb < 4 ? plan.log_nb : 4;
-  const size_t leaf_nodes_per_win = plan.nb >> L0_log;
-  if ((rc = e.nodes_a.reserve((size_t)gw * leaf_nodes_per_win * sizeof(Node<F>)))) return rc;
-  if ((rc = e.nodes_b.reserve((size_t)gw * (leaf_nodes_per_win / 2 + 1) * sizeof(Node<F>)))) return rc;
-  uint32_t* order = (uint32_t*)e.order.ptr;
-  uint32_t* bin_total = order + gb_max;
-  uint32_t* bin_start = bin_total + ORDER_BINS;
-  OrderCounters* oc = (OrderCounters*)(bin_start + ORDER_BINS);
-  OverflowTask* tasks = (OverflowTask*)e.tasks.ptr;
-  BigBucket* big = (BigBucket*)(tasks + max_tasks);
-  XYZZ<F>* task_partials = (XYZZ<F>*)e.task_partials.ptr;
-
-  g_stage.mark(1, s);
-  for (int g = 0; g < ngroups; g++) {
-    const int w1 = plan.nwin - g * gw, w0 = w1 - gw < 0 ? 0 : w1 - gw;   // windows [w0, w1), top group first
-    const int nw = w1 - w0;
-    const size_t b0 = (size_t)w0 * plan.nb, gb = (size_t)nw * plan.nb;
-    const unsigned gblk = blocks_for(gb, 1024);
-    // ---- stage A
-    CUDA_TRY(cudaMemsetAsync(bin_total, 0, 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters), s));
-    LAUNCH(k_order_hist, gblk, 1024, s, counts + b0, offsets + b0, (uint32_t)gb, cap, bin_total, oc, big, tasks);
-    LAUNCH(k_order_scan, 1, 1024, s, bin_total, bin_start);
-    LAUNCH(k_order_scatter, gblk, 1024, s, counts + b0, (uint32_t)gb, bin_start, order);
-    LAUNCH(k_accumulate<F>, blocks_for(gb, 128), 128, s, pts, entries, offsets + b0, counts + b0, order, (uint32_t)gb, cap, buckets + b0);
-    LAUNCH(k_accumulate_overflow<F>, blocks_for(max_tasks, 128), 128, s, pts, entries, tasks, oc, task_partials);
-    LAUNCH(k_merge_overflow<F>, blocks_for(max_tasks * 32, 128), 128, s, big, oc, task_partials, buckets + b0);
-    if (pipelined) {
-      CUDA_TRY(cudaEventRecord(e.ev_group[g], s));
-      CUDA_TRY(cudaStreamWaitEvent(t, e.ev_group[g], 0));
-    } else if (g == ngroups - 1) {
-      g_stage.mark(2, s);
-      if (g_profile.load()) {   // total sorted entries = non-zero digits D (algorithmic work of k_accumulate)
-        uint32_t last_off = 0, last_cnt = 0;
-        cudaMemcpyAsync(&last_off, offsets + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
-        cudaMemcpyAsync(&last_cnt, counts + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
-        cudaStreamSynchronize(s);
-        g_last_entries = (unsigned long long)last_off + last_cnt;
-      }
+  CUDA_TRY(cudaMemsetAsync(r.bin_total, 0, 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters), s));
+  LAUNCH(k_order_hist, nblk, 1024, s, r.counts, r.offsets, (uint32_t)nbt, cap, r.bin_total, r.oc, r.big, r.tasks);
+  LAUNCH(k_order_scan, 1, 1024, s, r.bin_total, r.bin_start);
+  LAUNCH(k_order_scatter, nblk, 1024, s, r.counts, (uint32_t)nbt, r.bin_start, r.order);
+  if (first) g_stage.mark(1, s);
+  LAUNCH(k_accumulate<F>, blocks_for(nbt, 128), 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap,
+         first ? 0 : 1, r.buckets);
+  const size_t tasks_bound = total_digits / cap + 2;
+  LAUNCH(k_accumulate_overflow<F>, blocks_for(tasks_bound, 128), 128, s, r.pts, r.entries, r.tasks, r.oc, r.task_partials);
+  LAUNCH(k_merge_overflow<F>, blocks_for(tasks_bound * 32, 128), 128, s, r.big, r.oc, r.task_partials, r.buckets);
+  if (first) {
+    g_stage.mark(2, s);
+    if (g_profile.load()) {   // total sorted entries = non-zero digits D (algorithmic work of k_accumulate)
+      uint32_t last_off = 0, last_cnt = 0;
+      cudaMemcpyAsync(&last_off, r.offsets + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(&last_cnt, r.counts + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      g_last_entries = (unsigned long long)last_off + last_cnt;
     }
-    // ---- stage B: reduction tree (leaf folds 2^L0_log buckets, inner levels fold up to 8 children)
-    Node<F>* cur = (Node<F>*)e.nodes_a.ptr;
-    Node<F>* nxt = (Node<F>*)e.nodes_b.ptr;
-    size_t nodes_per_win = leaf_nodes_per_win;
-    LAUNCH(k_reduce_leaf<F>, blocks_for(nw * nodes_per_win, 128), 128, t, buckets + b0, (uint32_t)(nw * nodes_per_win), 1 << L0_log, cur);
-    int log_cov = L0_log;                  // log2(buckets covered per node)
-    while (nodes_per_win > 1) {
-      int remaining_log = plan.log_nb - log_cov;
-      int l_log = remaining_log < 3 ? remaining_log : 3;
-      size_t out_per_win = nodes_per_win >> l_log;
-      LAUNCH(k_reduce_inner<F>, blocks_for(nw * out_per_win * COOP_LANES, 128), 128, t, cur, (uint32_t)(nw * out_per_win), 1 << l_log, log_cov, nxt);
-      Node<F>* tmp = cur; cur = nxt; nxt = tmp;
-      nodes_per_win = out_per_win;
-      log_cov += l_log;
-    }
-    if (!pipelined && g == ngroups - 1) g_stage.mark(3, s);
-    LAUNCH(k_window_combine<F>, 1, 32, t, cur, nw, plan.c, g == 0 ? 1 : 0, d_partial);
-  }
-  if (pipelined) {
-    CUDA_TRY(cudaEventRecord(e.ev_tail, t));
-    CUDA_TRY(cudaStreamWaitEvent(s, e.ev_tail, 0));
-  } else {
-    g_stage.mark(4, s);
   }
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
 }
 
+// bucket-reduction tree (leaf folds 2^L0_log buckets, inner levels fold up to 8 children), then the
+// Horner combine of the window sums.  (Overlapping this latency-bound tail with the accumulation of
+// other windows on a second stream was tried and measured slower: 11.7 vs 10.7 ms for 2^20 G1 -- the
+// dependent chains need the multiply pipe to themselves.)
+template <class F>
+static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s) {
+  const MsmPlan& plan = r.plan;
+  int rc;
+  int L0_log = plan.log_nb < 4 ? plan.log_nb : 4;
+  size_t nodes_per_win = plan.nb >> L0_log;
+  if ((rc = e.nodes_a.reserve((size_t)plan.nwin * nodes_per_win * sizeof(Node<F>)))) return rc;
+  if ((rc = e.nodes_b.reserve((size_t)plan.nwin * (nodes_per_win / 2 + 1) * sizeof(Node<F>)))) return rc;
+  Node<F>* cur = (Node<F>*)e.nodes_a.ptr;
+  Node<F>* nxt = (Node<F>*)e.nodes_b.ptr;
+  LAUNCH(k_reduce_leaf<F>, blocks_for(plan.nwin * nodes_per_win, 128), 128, s, r.buckets,
+         (uint32_t)(plan.nwin * nodes_per_win), 1 << L0_log, cur);
+  int log_cov = L0_log;                  // log2(buckets covered per node)
+  while (nodes_per_win > 1) {
+    int remaining_log = plan.log_nb - log_cov;
+    int l_log = remaining_log < 3 ? remaining_log : 3;
+    size_t out_per_win = nodes_per_win >> l_log;
+    LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win * COOP_LANES, 128), 128, s, cur,
+           (uint32_t)(plan.nwin * out_per_win), 1 << l_log, log_cov, nxt);
+    Node<F>* tmp = cur; cur = nxt; nxt = tmp;
+    nodes_per_win = out_per_win;
+    log_cov += l_log;
+  }
+  g_stage.mark(3, s);
+  LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan.nwin, plan.c, 1, d_partial);
+  g_stage.mark(4, s);
+  CUDA_TRY(cudaGetLastError());
+  return E_SUCCESS;
+}
+
+// device-resident input: one chunk
+template <class F>
+static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t index_base, XYZZ<F>* d_partial,
+                        unsigned long long* d_status, cudaStream_t s) {
+  MsmRun<F> r;
+  int rc;
+  if ((rc = msm_begin<F>(e, r, n, n))) return rc;
+  if ((rc = msm_feed<F>(e, r, d_raw, n, index_base, true, d_status, s))) return rc;
+  return msm_tail<F>(e, r, d_partial, s);
+}
+
+// host-resident input: stream it in chunks, copy of chunk i+1 overlapped with accumulation of chunk i
 template <class F>
 static int msm_host_impl(const unsigned char* in, size_t n, unsigned char* out) {
   Engine* ep;
@@ -279,16 +299,32 @@ static int msm_host_impl(const unsigned char* in, size_t n, unsigned char* out) 
   int prev;
   CUDA_TRY(cudaGetDevice(&prev));
   if (prev != e.device) CUDA_TRY(cudaSetDevice(e.device));
-  const size_t in_bytes = n * Wire<F>::PAIR_WORDS * 4, out_bytes = Wire<F>::POINT_WORDS * 4;
+  const size_t pair_bytes = Wire<F>::PAIR_WORDS * 4, out_bytes = Wire<F>::POINT_WORDS * 4;
+  const size_t in_bytes = n * pair_bytes;
   if ((rc = e.raw.reserve(in_bytes))) return rc;
   if ((rc = e.partial.reserve(sizeof(XYZZ<F>)))) return rc;
   if ((rc = e.out.reserve(out_bytes))) return rc;
   if ((rc = e.status.reserve(8))) return rc;
-  cudaStream_t s = e.stream;
-  CUDA_TRY(cudaMemcpyAsync(e.raw.ptr, in, in_bytes, cudaMemcpyHostToDevice, s));
+  cudaStream_t s = e.stream, cs = e.stream2;
+  const int nchunks = n >= (1u << 18) ? 8 : (n >= (1u << 16) ? 4 : 1);
+  const size_t chunk_n = (n + nchunks - 1) / nchunks;
+  MsmRun<F> r;
+  if ((rc = msm_begin<F>(e, r, n, chunk_n))) return rc;
   CUDA_TRY(cudaMemsetAsync(e.status.ptr, 0xFF, 8, s));
-  rc = msm_pipeline<F>(e, (const uint32_t*)e.raw.ptr, n, 0, (XYZZ<F>*)e.partial.ptr, (unsigned long long*)e.status.ptr, s);
-  if (rc) return rc;
+  for (int c = 0; c < nchunks; c++) {
+    const size_t lo = (size_t)c * chunk_n, hi = lo + chunk_n < n ? lo + chunk_n : n;
+    if (lo >= hi) break;
+    unsigned char* dst = (unsigned char*)e.raw.ptr + lo * pair_bytes;
+    if (nchunks == 1) {
+      CUDA_TRY(cudaMemcpyAsync(dst, in + lo * pair_bytes, (hi - lo) * pair_bytes, cudaMemcpyHostToDevice, s));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(dst, in + lo * pair_bytes, (hi - lo) * pair_bytes, cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(cudaEventRecord(e.ev_group[c], cs));
+      CUDA_TRY(cudaStreamWaitEvent(s, e.ev_group[c], 0));
+    }
+    if ((rc = msm_feed<F>(e, r, (const uint32_t*)dst, hi - lo, lo, c == 0, (unsigned long long*)e.status.ptr, s))) return rc;
+  }
+  if ((rc = msm_tail<F>(e, r, (XYZZ<F>*)e.partial.ptr, s))) return rc;
   LAUNCH(k_finalize<F>, 1, 32, s, (const XYZZ<F>*)e.partial.ptr, 1, (uint32_t*)e.out.ptr);
   CUDA_TRY(cudaMemcpyAsync(e.h_out, e.out.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(e.h_status, e.status.ptr, 8, cudaMemcpyDeviceToHost, s));

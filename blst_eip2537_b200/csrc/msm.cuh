@@ -269,16 +269,14 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
 }
 
 template <class F>
-__device__ __forceinline__ XYZZ<F> accumulate_segment(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
-                                                      uint32_t start, uint32_t cnt) {
-  XYZZ<F> acc = xyzz_inf<F>();
+__device__ __forceinline__ void accumulate_segment(XYZZ<F>& acc, const Affine<F>* __restrict__ pts,
+                                                   const uint32_t* __restrict__ entries, uint32_t start, uint32_t cnt) {
   for (uint32_t k = 0; k < cnt; k++) {
     uint32_t e = __ldg(entries + start + k);
     Affine<F> pt = load_affine(pts + (e & 0x7fffffffu));
     if (e >> 31) pt.y = neg(pt.y);
     xyzz_madd(acc, pt);
   }
-  return acc;
 }
 
 // one thread per bucket, buckets taken in order of decreasing size; at most `cap` entries each
@@ -286,12 +284,16 @@ template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                     const uint32_t* __restrict__ order, uint32_t nbuckets_total, uint32_t cap,
-                                                    XYZZ<F>* __restrict__ buckets) {
+                                                    int add_to_existing, XYZZ<F>* __restrict__ buckets) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nbuckets_total) return;
   uint32_t b = order[t];
   uint32_t cnt = counts[b];
-  buckets[b] = accumulate_segment(pts, entries, offsets[b], cnt < cap ? cnt : cap);
+  if (add_to_existing && cnt == 0) return;   // streamed chunks: the bucket keeps what earlier chunks left
+  XYZZ<F> acc;
+  if (add_to_existing) acc = buckets[b]; else acc = xyzz_inf<F>();
+  accumulate_segment(acc, pts, entries, offsets[b], cnt < cap ? cnt : cap);
+  buckets[b] = acc;
 }
 // one thread per overflow task
 template <class F>
@@ -301,7 +303,9 @@ __global__ void __launch_bounds__(128) k_accumulate_overflow(const Affine<F>* __
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= oc->ntasks) return;
   OverflowTask task = tasks[t];
-  partials[t] = accumulate_segment(pts, entries, task.start, task.len);
+  XYZZ<F> acc = xyzz_inf<F>();
+  accumulate_segment(acc, pts, entries, task.start, task.len);
+  partials[t] = acc;
 }
 // one warp per oversized bucket: lanes sum strided subsets of its partials, then a shuffle tree
 template <class F>
