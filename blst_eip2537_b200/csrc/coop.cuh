@@ -14,29 +14,42 @@
 namespace b200 {
 #ifdef __CUDACC__
 
-static constexpr int COOP_LANES = 8;
+// Group geometry: 8 product slots.  Over Fp a slot is one lane (group = 8 lanes).  Over Fp2 a slot
+// is 4 lanes, three of which compute the three Fp products of a Karatsuba Fp2 multiplication in
+// parallel (group = a full warp), so a G2 point operation also costs ~1 Fp-multiplication latency
+// per formula level instead of 3.
+template <class F> struct Coop;
+template <> struct Coop<Fp>  { static constexpr int LPS = 1, LANES = 8; };
+template <> struct Coop<Fp2> { static constexpr int LPS = 4, LANES = 32; };
 
 struct CoopGroup {
-  int lane;        // 0..7 inside the group
-  int base;        // warp lane of the group's lane 0
+  int lane;        // product slot 0..7 inside the group
+  int sub;         // lane inside the slot (Fp2: 0..3)
+  int base;        // warp lane of the group's first lane
+  int lps;         // lanes per slot
   unsigned mask;   // participating warp lanes
 };
+template <class F>
 __device__ __forceinline__ CoopGroup coop_group() {
   CoopGroup g;
-  int wl = threadIdx.x & 31;
-  g.lane = wl & (COOP_LANES - 1);
-  g.base = wl & ~(COOP_LANES - 1);
-  g.mask = 0xFFu << g.base;
+  const int wl = threadIdx.x & 31;
+  g.base = wl & ~(Coop<F>::LANES - 1);
+  const int in = wl - g.base;
+  g.lps = Coop<F>::LPS;
+  g.lane = in / Coop<F>::LPS;
+  g.sub = in % Coop<F>::LPS;
+  g.mask = Coop<F>::LANES == 32 ? 0xffffffffu : (0xFFu << g.base);
   return g;
 }
 
+// broadcast the value held by product slot `src` to every lane of the group
 template <class F>
 __device__ __forceinline__ F coop_bcast(const F& v, int src, const CoopGroup& g) {
   F r;
   const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
   uint32_t* d = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_sync(g.mask, s[i], g.base + src);
+  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_sync(g.mask, s[i], g.base + src * g.lps);
   return r;
 }
 template <class F>
@@ -45,6 +58,27 @@ __device__ __forceinline__ void coop_pick(F& dst, bool take, const F& v) {
   uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
 #pragma unroll
   for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = take ? s[i] : d[i];
+}
+// the slot's product a*b, available in every lane of the slot
+__device__ __forceinline__ Fp coop_product(const Fp& a, const Fp& b, const CoopGroup&) { return mul(a, b); }
+__device__ __forceinline__ Fp2 coop_product(const Fp2& a, const Fp2& b, const CoopGroup& g) {
+  // sub-lane 0: a0*b0, 1: a1*b1, 2 (and the spare 3): (a0+a1)*(b0+b1)
+  Fp x = add(a.c0, a.c1), y = add(b.c0, b.c1);
+  coop_pick(x, g.sub == 0, a.c0); coop_pick(y, g.sub == 0, b.c0);
+  coop_pick(x, g.sub == 1, a.c1); coop_pick(y, g.sub == 1, b.c1);
+  Fp t = mul(x, y);
+  const int slot0 = g.base + g.lane * 4;
+  Fp t0, t1, t2;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    t0.v[i] = __shfl_sync(g.mask, t.v[i], slot0);
+    t1.v[i] = __shfl_sync(g.mask, t.v[i], slot0 + 1);
+    t2.v[i] = __shfl_sync(g.mask, t.v[i], slot0 + 2);
+  }
+  Fp2 r;
+  r.c0 = sub(t0, t1);
+  r.c1 = sub(sub(t2, t0), t1);
+  return r;
 }
 
 // 2*p ; every lane of the group passes the same p and receives the same result
@@ -56,7 +90,7 @@ __device__ __noinline__ void coop_dbl(XYZZ<F>& p, const CoopGroup g) {
   // level 1: v = u^2, x2 = x^2
   F a = u;
   coop_pick(a, l == 1, p.x);
-  F r1 = sqr(a);
+  F r1 = coop_product(a, a, g);
   F v = coop_bcast(r1, 0, g), x2 = coop_bcast(r1, 1, g);
   F m = add(dbl(x2), x2);
   // level 2: w = u*v, s = x*v, mm = m*m, zz3 = v*zz
@@ -64,14 +98,14 @@ __device__ __noinline__ void coop_dbl(XYZZ<F>& p, const CoopGroup g) {
   coop_pick(a, l == 1, p.x);
   coop_pick(a, l == 2, m); coop_pick(b, l == 2, m);
   coop_pick(a, l == 3, p.zz);
-  F r2 = mul(a, b);
+  F r2 = coop_product(a, b, g);
   F w = coop_bcast(r2, 0, g), s = coop_bcast(r2, 1, g), mm = coop_bcast(r2, 2, g), zz3 = coop_bcast(r2, 3, g);
   F x3 = sub(mm, dbl(s));
   // level 3: ya = m*(s - x3), yb = w*y, zzz3 = w*zzz
   a = m; b = sub(s, x3);
   coop_pick(a, l == 1, w); coop_pick(b, l == 1, p.y);
   coop_pick(a, l == 2, w); coop_pick(b, l == 2, p.zzz);
-  F r3 = mul(a, b);
+  F r3 = coop_product(a, b, g);
   F ya = coop_bcast(r3, 0, g), yb = coop_bcast(r3, 1, g), zzz3 = coop_bcast(r3, 2, g);
   p.x = x3; p.y = sub(ya, yb); p.zz = zz3; p.zzz = zzz3;
 }
@@ -89,7 +123,7 @@ __device__ __noinline__ void coop_add(XYZZ<F>& acc, const XYZZ<F>& q, const Coop
   coop_pick(a, l == 3, q.y);     coop_pick(b, l == 3, acc.zzz);
   coop_pick(a, l == 4, acc.zz);  coop_pick(b, l == 4, q.zz);
   coop_pick(a, l == 5, acc.zzz); coop_pick(b, l == 5, q.zzz);
-  F r1 = mul(a, b);
+  F r1 = coop_product(a, b, g);
   F u1 = coop_bcast(r1, 0, g), u2 = coop_bcast(r1, 1, g), s1 = coop_bcast(r1, 2, g), s2 = coop_bcast(r1, 3, g);
   F zz12 = coop_bcast(r1, 4, g), zzz12 = coop_bcast(r1, 5, g);
   F p = sub(u2, u1), r = sub(s2, s1);
@@ -100,18 +134,18 @@ __device__ __noinline__ void coop_add(XYZZ<F>& acc, const XYZZ<F>& q, const Coop
   }
   // level 2: pp = p^2, rr = r^2
   a = p; coop_pick(a, l == 1, r);
-  F r2 = sqr(a);
+  F r2 = coop_product(a, a, g);
   F pp = coop_bcast(r2, 0, g), rr = coop_bcast(r2, 1, g);
   // level 3: ppp = p*pp, qq = u1*pp, zz3 = zz12*pp
   a = p; coop_pick(a, l == 1, u1); coop_pick(a, l == 2, zz12);
-  F r3 = mul(a, pp);
+  F r3 = coop_product(a, pp, g);
   F ppp = coop_bcast(r3, 0, g), qq = coop_bcast(r3, 1, g), zz3 = coop_bcast(r3, 2, g);
   F x3 = sub(sub(rr, ppp), dbl(qq));
   // level 4: ya = r*(qq - x3), yb = s1*ppp, zzz3 = zzz12*ppp
   a = r; b = sub(qq, x3);
   coop_pick(a, l == 1, s1);    coop_pick(b, l == 1, ppp);
   coop_pick(a, l == 2, zzz12); coop_pick(b, l == 2, ppp);
-  F r4 = mul(a, b);
+  F r4 = coop_product(a, b, g);
   F ya = coop_bcast(r4, 0, g), yb = coop_bcast(r4, 1, g), zzz3 = coop_bcast(r4, 2, g);
   acc.x = x3; acc.y = sub(ya, yb); acc.zz = zz3; acc.zzz = zzz3;
 }

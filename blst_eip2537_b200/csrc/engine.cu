@@ -123,14 +123,18 @@ static int engine_get(Engine** out, int device) {
 // ------------------------------------------------------------------------------------------
 // MSM
 // ------------------------------------------------------------------------------------------
-static int choose_window(size_t n) {
+// Window width.  Measured on B200 (tools/sweep_window.py, device-resident, every c in 3..16 at
+// n = 2^7 .. 2^20, G1 and G2): the optimum tracks log2(n) -- one thread per bucket needs both enough
+// buckets to fill the GPU and short per-bucket chains -- and flattens at 15-16 where the bucket
+// reduction starts to cost as much as it saves.  Within +-1 of the optimum the time changes by < 5 %.
+static int choose_window(size_t n, bool g2) {
+  (void)g2;
   int forced = g_forced_window.load();
   if (forced >= 2 && forced <= 16) return forced;
-  // Widths dividing 256 give a full-width top window, so no window degenerates into a handful of
-  // huge buckets (the top window is unsigned: it absorbs the last signed-digit carry).
-  if (n < 32) return 4;
-  if (n < (1u << 15)) return 8;
-  return 16;
+  int lg = 0;
+  while ((n >> (lg + 1)) != 0) lg++;
+  if (lg >= 20) return 16;
+  return lg < 7 ? 7 : (lg > 15 ? 15 : lg);
 }
 
 // optional per-stage timing (bench.py's roofline leg): events around the stages of the last MSM
@@ -165,7 +169,7 @@ struct MsmRun {
 
 template <class F>
 static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
-  r.plan = make_plan(choose_window(n_total));
+  r.plan = make_plan(choose_window(n_total, sizeof(F) == sizeof(Fp2)));
   const MsmPlan& plan = r.plan;
   r.nbt = (size_t)plan.nwin * plan.nb;   // total buckets, uniform layout
   r.chunk_cap = chunk_n;
@@ -264,14 +268,14 @@ static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s)
     int remaining_log = plan.log_nb - log_cov;
     int l_log = remaining_log < 3 ? remaining_log : 3;
     size_t out_per_win = nodes_per_win >> l_log;
-    LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win * COOP_LANES, 128), 128, s, cur,
+    LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win * Coop<F>::LANES, 128), 128, s, cur,
            (uint32_t)(plan.nwin * out_per_win), 1 << l_log, log_cov, nxt);
     Node<F>* tmp = cur; cur = nxt; nxt = tmp;
     nodes_per_win = out_per_win;
     log_cov += l_log;
   }
   g_stage.mark(3, s);
-  LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan.nwin, plan.c, 1, d_partial);
+  LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan, d_partial);
   g_stage.mark(4, s);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;

@@ -24,20 +24,35 @@
 
 namespace b200 {
 
+// Window layout.  The 256 scalar bits are cut into nwin = ceil(256/c) windows whose widths are c or
+// c-1 bits (so every c is usable, not only the divisors of 256).  All windows but the top one use
+// signed digits (|d| <= 2^(width-1)); the top window is unsigned and absorbs the last carry, so there
+// is no 257th-bit window.  When 256 is not a multiple of c the top window is one of the narrow ones
+// and needs exactly 2^(c-1) buckets like the others; when it is (c = 4, 8, 16) the top window has 2^c.
 struct MsmPlan {
-  int c;          // window width in bits (2..16)
+  int c;          // nominal window width in bits (2..16)
   int nwin;       // ceil(256 / c)
-  int top_bits;   // bits in the top window = 256 - c*(nwin-1)
-  int log_nb;     // log2(buckets per window) = max(c-1, top_bits)
-  uint32_t nb;    // buckets per window (uniform layout), power of two
+  int log_nb;     // log2(buckets per window), uniform layout
+  uint32_t nb;    // buckets per window, power of two
+  uint8_t width[128];    // bits of window w
+  uint16_t bitpos[128];  // first bit of window w
 };
 
 static inline MsmPlan make_plan(int c) {
   MsmPlan p;
   p.c = c;
   p.nwin = (256 + c - 1) / c;
-  p.top_bits = 256 - c * (p.nwin - 1);
-  p.log_nb = (c - 1 > p.top_bits) ? c - 1 : p.top_bits;
+  const int narrow = p.nwin * c - 256;           // windows that are c-1 bits wide (top window first)
+  int pos = 0;
+  for (int w = 0; w < p.nwin; w++) {
+    // narrow windows: the top one, then every other slot from the top down as needed
+    bool is_narrow = (p.nwin - 1 - w) < narrow;
+    p.width[w] = (uint8_t)(is_narrow ? c - 1 : c);
+  }
+  // (widths are assigned so that the narrow windows sit at the top; their sum is exactly 256)
+  for (int w = 0; w < p.nwin; w++) { p.bitpos[w] = (uint16_t)pos; pos += p.width[w]; }
+  const int top_w = p.width[p.nwin - 1];
+  p.log_nb = (c - 1 > top_w) ? c - 1 : top_w;
   p.nb = 1u << p.log_nb;
   return p;
 }
@@ -92,15 +107,15 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ raw
   for (int t = 0; t < (int)(sizeof(Affine<F>) / 4); t++) any |= pw[t];
   bool inf = (any == 0);
   uint32_t carry = 0;
-  const uint32_t half = 1u << (plan.c - 1);
   for (int w = 0; w < plan.nwin; w++) {
     int d;
+    const int wd = plan.width[w];
+    uint32_t raw_d = window_bits(k, plan.bitpos[w], wd) + carry;
     if (w < plan.nwin - 1) {
-      uint32_t raw_d = window_bits(k, w * plan.c, plan.c) + carry;
-      if (raw_d > half) { d = (int)raw_d - (int)(1u << plan.c); carry = 1; }
-      else              { d = (int)raw_d; carry = 0; }
+      if (raw_d > (1u << (wd - 1))) { d = (int)raw_d - (int)(1u << wd); carry = 1; }
+      else                          { d = (int)raw_d; carry = 0; }
     } else {
-      d = (int)(window_bits(k, w * plan.c, plan.top_bits) + carry);   // top window: unsigned, <= 2^top_bits
+      d = (int)raw_d;   // top window: unsigned, <= 2^width
     }
     if (inf) d = 0;
     digits[(size_t)w * n + i] = d;
@@ -355,8 +370,8 @@ __global__ void __launch_bounds__(128) k_reduce_leaf(const XYZZ<F>* __restrict__
 template <class F>
 __global__ void __launch_bounds__(128) k_reduce_inner(const Node<F>* __restrict__ in, uint32_t nout_total, int L, int log_m,
                                                       Node<F>* __restrict__ out) {
-  const CoopGroup g = coop_group();
-  uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) / COOP_LANES;
+  const CoopGroup g = coop_group<F>();
+  uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) / Coop<F>::LANES;
   if (t >= nout_total) return;
   const Node<F>* ch = in + (size_t)t * L;
   XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>(), wsum = xyzz_inf<F>();
@@ -369,23 +384,22 @@ __global__ void __launch_bounds__(128) k_reduce_inner(const Node<F>* __restrict_
   }
   for (int k = 0; k < log_m; k++) coop_dbl(acc, g);
   coop_add(wsum, acc, g);
-  if (g.lane == 0) { out[t].s = run; out[t].w = wsum; }
+  if (g.lane == 0 && g.sub == 0) { out[t].s = run; out[t].w = wsum; }
 }
 
-// Horner step over one group of windows (top group first): acc = 2^c * acc + T_w for the group's
-// windows from the top down, T_w = roots[w].w.  One group of 8 cooperating lanes walks the
-// sequential doublings (~240 in total over all groups).
+// Horner over the windows from the top down: acc = 2^width[w] * acc + T_w, T_w = roots[w].w.
+// One cooperative lane group walks the ~240 sequential doublings.
 template <class F>
-__global__ void k_window_combine(const Node<F>* __restrict__ roots, int nw, int c, int first, XYZZ<F>* __restrict__ acc_io) {
-  if (blockIdx.x != 0 || threadIdx.x >= COOP_LANES) return;
-  const CoopGroup g = coop_group();
-  XYZZ<F> acc = first ? xyzz_inf<F>() : *acc_io;
-  for (int w = nw - 1; w >= 0; w--) {
-    for (int k = 0; k < c; k++) coop_dbl(acc, g);
+__global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan, XYZZ<F>* __restrict__ acc_io) {
+  if (blockIdx.x != 0 || threadIdx.x >= Coop<F>::LANES) return;
+  const CoopGroup g = coop_group<F>();
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (int w = plan.nwin - 1; w >= 0; w--) {
+    for (int k = 0; k < plan.width[w]; k++) coop_dbl(acc, g);   // acc is still infinity for the top window
     XYZZ<F> t = roots[w].w;
     coop_add(acc, t, g);
   }
-  if (g.lane == 0) *acc_io = acc;
+  if (g.lane == 0 && g.sub == 0) *acc_io = acc;
 }
 
 // sum `count` partial results (multi-GPU gather, or count = 1), convert to affine, encode

@@ -68,7 +68,6 @@ static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, 
   size_t nbt = (size_t)plan.nwin * plan.nb;
   XYZZ<F>* buckets = new XYZZ<F>[nbt];
   for (size_t b = 0; b < nbt; b++) buckets[b] = xyzz_inf<F>();
-  const uint32_t half = 1u << (plan.c - 1);
   for (size_t i = 0; i < n; i++) {
     uint32_t w[SW];
     load_words(w, in + 4 * SW * i, SW);
@@ -87,10 +86,11 @@ static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, 
         if (sh + cc > 32 && word + 1 < 8) v |= k[word + 1] << (32 - sh);
         return v & ((1u << cc) - 1);
       };
+      const int wd = plan.width[win];
+      uint32_t raw_d = bits(plan.bitpos[win], wd) + carry;
       if (win < plan.nwin - 1) {
-        uint32_t raw_d = bits(win * plan.c, plan.c) + carry;
-        if (raw_d > half) { d = (int)raw_d - (int)(1u << plan.c); carry = 1; } else { d = (int)raw_d; carry = 0; }
-      } else d = (int)(bits(win * plan.c, plan.top_bits) + carry);
+        if (raw_d > (1u << (wd - 1))) { d = (int)raw_d - (int)(1u << wd); carry = 1; } else { d = (int)raw_d; carry = 0; }
+      } else d = (int)raw_d;
       if (!d) continue;
       uint32_t mag = d < 0 ? -d : d;
       Affine<F> q = p;
@@ -122,9 +122,9 @@ static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, 
     }
     delete[] cur; cur = nxt; npw = opw; log_cov += l_log;
   }
-  XYZZ<F> acc = cur[plan.nwin - 1].w;
-  for (int win = plan.nwin - 2; win >= 0; win--) {
-    for (int q = 0; q < plan.c; q++) acc = xyzz_dbl(acc);
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (int win = plan.nwin - 1; win >= 0; win--) {
+    for (int q = 0; q < plan.width[win]; q++) acc = xyzz_dbl(acc);
     xyzz_add(acc, cur[win].w);
   }
   Affine<F> a = xyzz_to_affine(acc);

@@ -37,7 +37,7 @@ def gen_g1(n):
 
 
 if "msm" in what:
-    for logn in (10, 14, 16, 18, 20):
+    for logn in (7, 10, 12, 14, 16, 18, 20):
         n = 1 << logn
         t0 = time.time(); data = gen_g1(n); tg = time.time() - t0
         h = torch.from_numpy(data).pin_memory()
@@ -48,7 +48,7 @@ if "msm" in what:
         d_st = torch.zeros(1, dtype=torch.int64, device="cuda")
         s = torch.cuda.current_stream().cuda_stream
         torch.cuda.synchronize()
-        for c in ((0,) if logn < 16 else (0, 12, 13, 14, 15, 16)):
+        for c in (0,):
             b.set_window(c)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for rep in range(3):
