@@ -81,7 +81,7 @@ struct Engine {
   // MSM workspaces
   Buffer raw, pts, digits, counts, offsets, block_sums, entries, buckets, nodes_a, nodes_b, partial, out, status, order, tasks, task_partials;
   // pairing workspaces
-  Buffer pr_raw, pr_offsets, pr_pair_call, pr_call_first, pr_g1, pr_g2, pr_status, pr_f, pr_outs, pr_errs;
+  Buffer pr_raw, pr_offsets, pr_lines, pr_tasks, pr_g1, pr_g2, pr_status, pr_f, pr_outs, pr_errs;
   unsigned char* h_out = nullptr;            // pinned: result bytes
   unsigned long long* h_status = nullptr;    // pinned
 };
@@ -493,17 +493,29 @@ extern "C" EIP2537_ERROR bls12_b200_g2_generator_mul(byte* out, const byte* scal
 static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const unsigned long long* d_offsets, size_t n_calls,
                                      size_t total_pairs, uint32_t* d_outs, int* d_errs, cudaStream_t s) {
   int rc;
+  const size_t max_tasks = total_pairs;    // every chunk holds at least one pair
+  if (total_pairs > (4u << 20)) { snprintf(g_last_error, sizeof g_last_error, "pairing batch too large: split it"); return E_MEMORY; }
   if ((rc = e.pr_g1.reserve(total_pairs * sizeof(G1Affine)))) return rc;
   if ((rc = e.pr_g2.reserve(total_pairs * sizeof(G2Affine)))) return rc;
-  if ((rc = e.pr_status.reserve(total_pairs * sizeof(int)))) return rc;
+  if ((rc = e.pr_status.reserve(total_pairs * sizeof(int) + total_pairs + 64))) return rc;
+  if ((rc = e.pr_lines.reserve((size_t)ML_STEPS * total_pairs * sizeof(Line)))) return rc;
+  if ((rc = e.pr_tasks.reserve(max_tasks * sizeof(PairingTask) + n_calls * sizeof(uint32_t) + 64))) return rc;
+  if ((rc = e.pr_f.reserve(max_tasks * sizeof(Fp12)))) return rc;
   G1Affine* g1 = (G1Affine*)e.pr_g1.ptr;
   G2Affine* g2 = (G2Affine*)e.pr_g2.ptr;
   int* pstat = (int*)e.pr_status.ptr;
-  LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
-  if ((rc = e.pr_f.reserve(total_pairs * sizeof(Fp12)))) return rc;
+  unsigned char* skip = (unsigned char*)(pstat + total_pairs);
+  Line* lines = (Line*)e.pr_lines.ptr;
+  uint32_t* ntasks = (uint32_t*)e.pr_tasks.ptr;
+  PairingTask* tasks = (PairingTask*)(ntasks + 16);
+  uint32_t* call_first = (uint32_t*)(tasks + max_tasks);
   Fp12* f = (Fp12*)e.pr_f.ptr;
-  LAUNCH(k_pairing_miller, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, f);
-  LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, d_offsets, n_calls, pstat, f, d_outs, d_errs);
+  CUDA_TRY(cudaMemsetAsync(ntasks, 0, 64, s));
+  LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
+  LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
+  LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, ntasks, tasks, call_first, d_errs);
+  LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, ntasks, lines, skip, total_pairs, f);
+  LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, call_first, f, d_outs, d_errs);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
 }
@@ -774,7 +786,7 @@ extern "C" void bls12_b200_shutdown(void) {
     cudaStreamSynchronize(e.stream);
     Buffer* bufs[] = {&e.raw, &e.pts, &e.digits, &e.counts, &e.offsets, &e.block_sums, &e.entries, &e.buckets,
                       &e.nodes_a, &e.nodes_b, &e.partial, &e.out, &e.status, &e.order, &e.tasks, &e.task_partials, &e.pr_raw, &e.pr_offsets,
-                      &e.pr_pair_call, &e.pr_call_first, &e.pr_g1, &e.pr_g2, &e.pr_status, &e.pr_f, &e.pr_outs, &e.pr_errs};
+                      &e.pr_lines, &e.pr_tasks, &e.pr_g1, &e.pr_g2, &e.pr_status, &e.pr_f, &e.pr_outs, &e.pr_errs};
     for (Buffer* b : bufs) b->release();
     cudaFreeHost(e.h_out);
     cudaFreeHost(e.h_status);

@@ -259,7 +259,7 @@ __global__ void k_pairing_index(const unsigned long long* __restrict__ offsets, 
 
 // one thread per pair: decode + subgroup checks in the reference's order
 // (G1 decode, G1 subgroup, G2 decode, G2 subgroup; eip2537.c:1036-1053); status[j] = first failing code
-__global__ void __launch_bounds__(64) k_pairing_decode(const uint32_t* __restrict__ raw, size_t total_pairs,
+__global__ void __launch_bounds__(64, 6) k_pairing_decode(const uint32_t* __restrict__ raw, size_t total_pairs,
                                                        G1Affine* __restrict__ g1, G2Affine* __restrict__ g2, int* __restrict__ status) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= total_pairs) return;
@@ -282,41 +282,119 @@ __global__ void __launch_bounds__(64) k_pairing_decode(const uint32_t* __restric
   if (code == E_SUCCESS) { g1[j] = p; g2[j] = q; }
 }
 
-// one thread per pair: single-pair Miller loop, as the reference runs them (eip2537.c:1060/:1065),
-// result parked in HBM (576 B per pair) for the per-call product
-__global__ void __launch_bounds__(64) k_pairing_miller(const G1Affine* __restrict__ g1, const G2Affine* __restrict__ g2,
-                                                       const int* __restrict__ status, size_t total_pairs, Fp12* __restrict__ f) {
+// ---- Miller loop, split in two kernels -------------------------------------------------------
+// The reference runs k independent single-pair Miller loops per call and multiplies them
+// (eip2537.c:1060-1065).  Only the boolean is observable, so here the pairs of a call share the
+// Fp12 squarings (a multi-Miller loop), and the work is cut along its natural seam:
+//   k_pairing_lines       one thread per PAIR: walks T = [.]Q on the twist and writes the 68 line
+//                         functions, already evaluated at P (3 Fp2 = 288 B each), to HBM.  Small
+//                         state (T, Q, P), no Fp12.
+//   k_pairing_accumulate  one thread per CHUNK of <= PAIRING_CHUNK pairs of one call:
+//                         f <- f^2 * prod(lines) step by step: one Fp12 squaring per step per chunk
+//                         instead of per pair, 13 Fp2 products per line.
+//   k_pairing_calls       one thread per call: product of its chunks, final exponentiation, is-one.
+static constexpr int PAIRING_CHUNK = 3;
+static constexpr int ML_STEPS = 68;          // 63 doubling steps + 5 addition steps (|z| has weight 6)
+
+struct Line { Fp2 l0, l1, l4; };             // l0 + l1*w^2 + l4*w^3, already multiplied by xP / yP
+struct PairingTask { uint32_t first_pair, npairs; };
+
+__global__ void __launch_bounds__(64, 6) k_pairing_lines(const G1Affine* __restrict__ g1, const G2Affine* __restrict__ g2,
+                                                      const int* __restrict__ status, size_t total_pairs,
+                                                      Line* __restrict__ lines, unsigned char* __restrict__ skip) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= total_pairs) return;
-  if (status[j] != E_SUCCESS) return;
+  if (status[j] != E_SUCCESS) { skip[j] = 1; return; }
   G1Affine p = g1[j];
   G2Affine q = g2[j];
-  Fp12 acc;
-  miller_loop(acc, p, q);
-  f[j] = acc;
+  if (is_inf(p) || is_inf(q)) { skip[j] = 1; return; }   // contributes 1
+  skip[j] = 0;
+  G2Proj t;
+  t.x = q.x; t.y = q.y; t.z = fp2_one();
+  int s = 0;
+  for (int i = 62; i >= 0; i--) {
+    Line ln;
+    ml_dbl_step(t, ln.l0, ln.l1, ln.l4);
+    ln.l1 = mulfpo(ln.l1, p.x); ln.l4 = mulfpo(ln.l4, p.y);
+    lines[(size_t)s * total_pairs + j] = ln;
+    s++;
+    if ((B200_Z_ABS >> i) & 1) {
+      ml_add_step(t, q, ln.l0, ln.l1, ln.l4);
+      ln.l1 = mulfpo(ln.l1, p.x); ln.l4 = mulfpo(ln.l4, p.y);
+      lines[(size_t)s * total_pairs + j] = ln;
+      s++;
+    }
+  }
 }
 
-// one thread per call: first failing pair decides the error; otherwise product of the pairs'
-// Miller values (blst_fp12_mul, :1061), one final exponentiation (:1070), is-one -> out[31] (:1076)
-__global__ void __launch_bounds__(64) k_pairing_calls(const unsigned long long* __restrict__ offsets, size_t n_calls,
-                                                      const int* __restrict__ status, const Fp12* __restrict__ f,
-                                                      uint32_t* __restrict__ outs, int* __restrict__ errs) {
+// one thread per call: decide the call's error code (first failing pair, eip2537.c:1033-1053) and cut
+// the call into chunks for k_pairing_accumulate
+__global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* __restrict__ offsets, size_t n_calls,
+                                                      const int* __restrict__ status, uint32_t* ntasks,
+                                                      PairingTask* __restrict__ tasks, uint32_t* __restrict__ call_first_task,
+                                                      int* __restrict__ errs) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_calls) return;
   size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
-  uint32_t* out = outs + 8 * i;
-  for (int k = 0; k < 8; k++) out[k] = 0;
   if (first == last) { errs[i] = E_INVALID_LENGTH; return; }
   for (size_t j = first; j < last; j++)
     if (status[j] != E_SUCCESS) { errs[i] = status[j]; return; }
-  Fp12 acc = f[first], cur;
-  for (size_t j = first + 1; j < last; j++) {
-    cur = f[j];
+  errs[i] = E_SUCCESS;
+  uint32_t k = (uint32_t)(last - first), nch = (k + PAIRING_CHUNK - 1) / PAIRING_CHUNK;
+  uint32_t base = atomicAdd(ntasks, nch);
+  call_first_task[i] = base;
+  for (uint32_t c = 0; c < nch; c++) {
+    uint32_t lo = c * PAIRING_CHUNK, len = k - lo < PAIRING_CHUNK ? k - lo : PAIRING_CHUNK;
+    tasks[base + c] = PairingTask{(uint32_t)first + lo, len};
+  }
+}
+
+__global__ void __launch_bounds__(64, 6) k_pairing_accumulate(const PairingTask* __restrict__ tasks, const uint32_t* __restrict__ ntasks,
+                                                           const Line* __restrict__ lines, const unsigned char* __restrict__ skip,
+                                                           size_t total_pairs, Fp12* __restrict__ fchunk) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *ntasks) return;
+  PairingTask task = tasks[t];
+  Fp12 f;
+  fp12_set_one(f);
+  bool started = false;
+  int s = 0;
+  for (int i = 62; i >= 0; i--) {
+    if (started) fp12_sqr(f, f);
+    const int nsteps = ((B200_Z_ABS >> i) & 1) ? 2 : 1;
+    for (int a = 0; a < nsteps; a++, s++) {
+      for (uint32_t k = 0; k < task.npairs; k++) {
+        size_t j = task.first_pair + k;
+        if (skip[j]) continue;
+        Line ln = lines[(size_t)s * total_pairs + j];
+        fp12_mul_by_014(f, ln.l0, ln.l1, ln.l4);
+        started = true;
+      }
+    }
+  }
+  fp12_conj(f, f);
+  fchunk[t] = f;
+}
+
+// one thread per call: product of the chunks' Miller values (blst_fp12_mul, :1061), one final
+// exponentiation (:1070), is-one -> out[31] (:1076)
+__global__ void __launch_bounds__(64) k_pairing_calls(size_t n_calls, const unsigned long long* __restrict__ offsets,
+                                                      const uint32_t* __restrict__ call_first_task, const Fp12* __restrict__ fchunk,
+                                                      uint32_t* __restrict__ outs, const int* __restrict__ errs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_calls) return;
+  uint32_t* out = outs + 8 * i;
+  for (int k = 0; k < 8; k++) out[k] = 0;
+  if (errs[i] != E_SUCCESS) return;
+  uint32_t npairs = (uint32_t)(offsets[i + 1] / 384 - offsets[i] / 384), nch = (npairs + PAIRING_CHUNK - 1) / PAIRING_CHUNK;
+  uint32_t base = call_first_task[i];
+  Fp12 acc = fchunk[base], cur;
+  for (uint32_t c = 1; c < nch; c++) {
+    cur = fchunk[base + c];
     fp12_mul(acc, acc, cur);
   }
   final_exp(acc, acc);
   if (fp12_is_one(acc)) out[7] = 0x01000000u;   // byte 31 of the 32-byte big-endian word
-  errs[i] = E_SUCCESS;
 }
 #endif  // __CUDACC__
 
