@@ -120,7 +120,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -388,19 +388,18 @@ def run_ours(args, rank, world, local_rank):
                 flush.fill_(1)
 
         # ---------------- device-resident timing (value)
+        sampler.start()
         for _ in range(max(args.warmup, 3)):
             flush_l2(); step_device()
         barrier()
         ok = check()
         launches0 = b.launch_count()
-        sampler.start()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         for e0, e1 in evs:
             flush_l2()
             e0.record(); step_device(); e1.record()
         barrier()
-        clocks = sampler.stop()
         launches = b.launch_count() - launches0
         dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
         t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -422,6 +421,7 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = units_per_step * args.steps / float(t.item())
+        clocks = sampler.stop()     # sampled from the first warm-up step to the last end-to-end step
 
         # ---------------- roofline of the dominant kernel (rank 0, live CUDA events inside the engine)
         roofline = None
@@ -453,14 +453,52 @@ def run_ours(args, rank, world, local_rank):
                 achieved = mac / (float(np.mean(acc_ms)) * 1e-3)
                 hbm = json.load(open(PEAKS_FILE))["hbm_gbs"] if os.path.exists(PEAKS_FILE) else 6650.0
                 point_bytes = digits * (96 if group == 1 else 192)
+                traffic = None
+                tf = os.path.join(ROOT, "profiles", "r01_accumulate_traffic.json")
+                if os.path.exists(tf):   # dram bytes of one k_accumulate launch, from the committed `ncu --set full` capture
+                    traffic = json.load(open(tf)).get("g%d_2p%d" % (group, args.logn))
                 roofline = {
                     "bound": "int32-mad", "kernel": "k_accumulate", "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
-                    "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": None,
+                    "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": traffic,
                     "peak_source": "measured live: best of two IMAD.WIDE.U32 issue-rate probes (independent accumulators / carry-chained rows), 148x2048 threads; theoretical 32 lanes/clk/SM x 148 SM x 1.965 GHz = 9.3 TMAC32/s (MEASURED_PEAKS.json has no integer peak)",
                     "algorithmic": "%d point additions x %d Fp-mul x 300 MAC32" % (digits, fme),
                     "hbm_secondary": {"achieved_gbs": point_bytes / (float(np.mean(acc_ms)) * 1e-3) / 1e9, "peak_gbs": hbm,
                                       "peak_source": "MEASURED_PEAKS.json" if os.path.exists(PEAKS_FILE) else "fallback"},
                 }
+
+        if args.workload == "pairing" and rank == 0:
+            # Fp-multiplication counts of the GPU's own formulas, measured with the host-emulation build
+            # (tests/test_host_emul.py::test_pairing_fme_constants pins them): per pair 2986 (decode + G1/G2
+            # subgroup checks) + 2221 (68 line functions) + 2652 (68 sparse Fp12 products); per chunk of <= 3
+            # pairs 2232 (62 Fp12 squarings); per call 7688 (final exponentiation) + 54 per extra chunk.
+            ks = [2 + ((rank * calls + j) % 15) for j in range(calls)]
+            nch = [(k + 2) // 3 for k in ks]
+            fme = {"decode": 2986 * sum(ks), "lines": 2221 * sum(ks), "accumulate": 2652 * sum(ks) + 2232 * sum(nch),
+                   "calls": sum(7688 + 54 * (c - 1) for c in nch)}
+            L.bls12_b200_set_profile(1)
+            st = (ctypes.c_float * 4)()
+            stage = []
+            for _ in range(3):
+                flush_l2(); step_device(); torch.cuda.synchronize()
+                if L.bls12_b200_last_pairing_profile(st) == 0:
+                    stage.append([st[0], st[1], st[2], st[3]])
+            L.bls12_b200_set_profile(0)
+            ms = ctypes.c_float()
+            nthr = 148 * 2048
+            L.bls12_b200_fp_microbench(1, nthr, 2000, ctypes.byref(ms), None)
+            peak_plain = nthr * 2000 * 64 / (ms.value * 1e-3)
+            L.bls12_b200_fp_microbench(2, nthr, 2000, ctypes.byref(ms), None)
+            peak_mac = max(peak_plain, nthr * 2000 * 24 / (ms.value * 1e-3))
+            if stage:
+                avg = np.mean(np.asarray(stage), axis=0)
+                extra["stage_ms"] = {"decode_subgroup": float(avg[0]), "lines": float(avg[1]), "accumulate": float(avg[2]), "final_exp": float(avg[3])}
+                extra["stage_frac_of_peak"] = {k: fme[k] * FME_MAC32 / (float(avg[i]) * 1e-3) / peak_mac for i, k in enumerate(("decode", "lines", "accumulate", "calls"))}
+                achieved = fme["accumulate"] * FME_MAC32 / (float(avg[2]) * 1e-3)
+                roofline = {"bound": "int32-mad", "kernel": "k_pairing_accumulate", "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
+                            "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": None,
+                            "peak_source": "measured live: best of two IMAD.WIDE.U32 issue-rate probes",
+                            "algorithmic": "%d Fp-mul x 300 MAC32 (counted on the host-emulation build of the same source)" % fme["accumulate"],
+                            "whole_step_frac": sum(fme.values()) * FME_MAC32 / (dev_ms / args.steps * 1e-3) / peak_mac}
 
         # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
         cpu_baseline = None
@@ -479,7 +517,8 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "pairing" else "weak", "vs_baseline": None,
             "dtype": "u32 limbs (12x32 Montgomery, IMAD.WIDE)", "data": "synthetic",
             "config": dict({"workload": workload_name(args), "l2": "inputs larger than L2" if flush is None else "L2 flushed between steps (256 MiB fill)",
                             "parallelism": "points sharded, NCCL all-gather of partial sums" if args.workload != "pairing" else "calls sharded, no collective",

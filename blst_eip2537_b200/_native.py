@@ -33,7 +33,7 @@ EXT_FUNCTIONS = [
     "bls12_b200_init", "bls12_b200_shutdown", "bls12_b200_last_error", "bls12_b200_launch_count",
     "bls12_b200_set_window", "bls12_pairing_batch", "bls12_b200_msm_device", "bls12_b200_msm_partial_device",
     "bls12_b200_msm_combine_device", "bls12_b200_pairing_batch_device", "bls12_b200_g1_generator_mul",
-    "bls12_b200_g2_generator_mul", "bls12_b200_fp_microbench", "bls12_b200_selftest", "bls12_b200_partial_bytes", "bls12_b200_set_profile", "bls12_b200_last_msm_profile",
+    "bls12_b200_g2_generator_mul", "bls12_b200_fp_microbench", "bls12_b200_selftest", "bls12_b200_partial_bytes", "bls12_b200_set_profile", "bls12_b200_last_msm_profile", "bls12_b200_last_pairing_profile",
 ]
 
 
@@ -95,5 +95,7 @@ def lib() -> ctypes.CDLL:
     L.bls12_b200_last_msm_profile.argtypes = [vp, vp]
     L.bls12_b200_partial_bytes.restype = sz
     L.bls12_b200_partial_bytes.argtypes = [i32]
+    L.bls12_b200_last_pairing_profile.restype = i32
+    L.bls12_b200_last_pairing_profile.argtypes = [vp]
     _LIB = L
     return L

@@ -152,6 +152,7 @@ struct StageTimer {
   }
 };
 static StageTimer g_stage;
+static StageTimer g_pstage;   // pairing: decode | lines | plan+accumulate | calls
 static unsigned long long g_last_entries = 0;
 
 // The MSM runs in three phases so that a host-resident input can be STREAMED: bucket accumulation is
@@ -511,11 +512,16 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   uint32_t* call_first = (uint32_t*)(tasks + max_tasks);
   Fp12* f = (Fp12*)e.pr_f.ptr;
   CUDA_TRY(cudaMemsetAsync(ntasks, 0, 64, s));
+  g_pstage.mark(0, s);
   LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
+  g_pstage.mark(1, s);
   LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
+  g_pstage.mark(2, s);
   LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, ntasks, tasks, call_first, d_errs);
   LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, ntasks, lines, skip, total_pairs, f);
+  g_pstage.mark(3, s);
   LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, call_first, f, d_outs, d_errs);
+  g_pstage.mark(4, s);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
 }
@@ -800,6 +806,13 @@ extern "C" void bls12_b200_shutdown(void) {
 extern "C" const char* bls12_b200_last_error(void) { return g_last_error; }
 extern "C" uint64_t bls12_b200_launch_count(void) { return g_launches.load(); }
 extern "C" void bls12_b200_set_window(int c) { g_forced_window.store(c); }
+// stage_ms4 = {decode + subgroup checks, line functions, chunked accumulate, product + final exp}
+extern "C" EIP2537_ERROR bls12_b200_last_pairing_profile(float* stage_ms4) {
+  if (g_pstage.used < 5) return EIP2537_EMPTY_INPUT;
+  CUDA_TRY2(cudaEventSynchronize(g_pstage.ev[4]));
+  for (int i = 0; i < 4; i++) CUDA_TRY2(cudaEventElapsedTime(&stage_ms4[i], g_pstage.ev[i], g_pstage.ev[i + 1]));
+  return EIP2537_SUCCESS;
+}
 extern "C" size_t bls12_b200_partial_bytes(int group) { return group == 1 ? sizeof(XYZZ<Fp>) : sizeof(XYZZ<Fp2>); }
 extern "C" void bls12_b200_set_profile(int on) { g_profile.store(on); }
 // stage_ms[4] = {decode+digits+sort, accumulate, bucket reduce tree, window combine} of the last profiled MSM

@@ -310,7 +310,13 @@ B200_D Fp mul(const Fp& a, const Fp& b_in) {
 #else
 B200_HD Fp mul(const Fp& a, const Fp& b);
 #endif
+#ifdef B200_COUNT_MULS
+extern unsigned long long g_fp_mul_count;   // tests/host_emul only: counts Fp multiplications per phase
+#endif
 B200_HD Fp mul_portable(const Fp& a, const Fp& b) {
+#ifdef B200_COUNT_MULS
+  g_fp_mul_count++;
+#endif
   const uint32_t* p = C_P();
   uint32_t t[14];
 #pragma unroll

@@ -247,6 +247,12 @@ B200_HD_NI bool g2_in_subgroup(const G2Affine& p) {
   return eq(mulo(px, q.zz), q.x) && eq(mulo(py, q.zzz), neg(q.y));   // [z]Q = -[|z|]Q
 }
 
+static constexpr int PAIRING_CHUNK = 3;
+static constexpr int ML_STEPS = 68;          // 63 doubling steps + 5 addition steps (|z| has weight 6)
+
+struct Line { Fp2 l0, l1, l4; };             // l0 + l1*w^2 + l4*w^3, already multiplied by xP / yP
+struct PairingTask { uint32_t first_pair, npairs; };
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- kernels
 // pair_call[j] = index of the call that owns pair j   (offsets are byte offsets, 384 B per pair)
@@ -293,11 +299,6 @@ __global__ void __launch_bounds__(64, 6) k_pairing_decode(const uint32_t* __rest
 //                         f <- f^2 * prod(lines) step by step: one Fp12 squaring per step per chunk
 //                         instead of per pair, 13 Fp2 products per line.
 //   k_pairing_calls       one thread per call: product of its chunks, final exponentiation, is-one.
-static constexpr int PAIRING_CHUNK = 3;
-static constexpr int ML_STEPS = 68;          // 63 doubling steps + 5 addition steps (|z| has weight 6)
-
-struct Line { Fp2 l0, l1, l4; };             // l0 + l1*w^2 + l4*w^3, already multiplied by xP / yP
-struct PairingTask { uint32_t first_pair, npairs; };
 
 __global__ void __launch_bounds__(64, 6) k_pairing_lines(const G1Affine* __restrict__ g1, const G2Affine* __restrict__ g2,
                                                       const int* __restrict__ status, size_t total_pairs,

@@ -76,6 +76,9 @@ EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, fl
  *      and the number of non-zero signed digits (= point additions done by the accumulate kernel) */
 void bls12_b200_set_profile(int on);
 EIP2537_ERROR bls12_b200_last_msm_profile(float* stage_ms4, uint64_t* nonzero_digits);
+/* same for the pairing batch: stage_ms4 = {decode + subgroup checks, line functions,
+ * chunked multi-Miller accumulate, Fp12 product + final exponentiation} */
+EIP2537_ERROR bls12_b200_last_pairing_profile(float* stage_ms4);
 
 /* ---- on-device self test of the PTX field arithmetic against portable C++ on n pseudo-random
  *      inputs; mismatches4 = {mul, add, sub, inv} mismatch counts (all must be 0) */

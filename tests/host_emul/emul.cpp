@@ -4,6 +4,8 @@
 // (engine.cu launches kernels only); on the host the portable 64-bit Fp multiply stands in for
 // the PTX carry-chain one, everything above it is the same source the GPU runs.
 #include <cstring>
+#define B200_COUNT_MULS 1
+namespace b200 { unsigned long long g_fp_mul_count = 0; }
 #include "../../blst_eip2537_b200/csrc/msm.cuh"
 #include "../../blst_eip2537_b200/csrc/pairing.cuh"
 
@@ -162,6 +164,89 @@ int emul_pairing(unsigned char* out32, unsigned char* gt576, const unsigned char
     for (int i = 0; i < 12; i++) { uint32_t w[16]; fp_to_slot(w, e[i]); memcpy(gt576 + 48 * i, (unsigned char*)w + 16, 48); }
   }
   return 0;
+}
+// Fp-multiplication counts of the GPU's own pairing formulas, phase by phase, for one call of k pairs
+// (same source as k_pairing_decode / k_pairing_lines / k_pairing_accumulate / k_pairing_calls):
+// counts[0] decode + subgroup checks, [1] line functions, [2] chunked accumulate, [3] product + final exp
+int emul_pairing_fme_counts(unsigned long long* counts, unsigned char* out32, const unsigned char* in, size_t k) {
+  G1Affine* ps = new G1Affine[k];
+  G2Affine* qs = new G2Affine[k];
+  unsigned long long c0 = g_fp_mul_count;
+  for (size_t j = 0; j < k; j++) {
+    uint32_t w[96];
+    load_words(w, in + 384 * j, 96);
+    int code = decode_point(ps[j], w);
+    if (code == 0 && !g1_in_subgroup(ps[j])) code = E_NOT_IN_SUBGROUP;
+    if (code == 0) code = decode_point(qs[j], w + 32);
+    if (code == 0 && !g2_in_subgroup(qs[j])) code = E_NOT_IN_SUBGROUP;
+    if (code) { delete[] ps; delete[] qs; return code; }
+  }
+  counts[0] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  Line* lines = new Line[ML_STEPS * k];
+  bool* skip = new bool[k];
+  for (size_t j = 0; j < k; j++) {
+    skip[j] = is_inf(ps[j]) || is_inf(qs[j]);
+    if (skip[j]) continue;
+    G2Proj t; t.x = qs[j].x; t.y = qs[j].y; t.z = fp2_one();
+    int s = 0;
+    for (int i = 62; i >= 0; i--) {
+      Line ln;
+      ml_dbl_step(t, ln.l0, ln.l1, ln.l4);
+      ln.l1 = mulfpo(ln.l1, ps[j].x); ln.l4 = mulfpo(ln.l4, ps[j].y);
+      lines[s++ * k + j] = ln;
+      if ((B200_Z_ABS >> i) & 1) {
+        ml_add_step(t, qs[j], ln.l0, ln.l1, ln.l4);
+        ln.l1 = mulfpo(ln.l1, ps[j].x); ln.l4 = mulfpo(ln.l4, ps[j].y);
+        lines[s++ * k + j] = ln;
+      }
+    }
+  }
+  counts[1] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  size_t nch = (k + PAIRING_CHUNK - 1) / PAIRING_CHUNK;
+  Fp12* fch = new Fp12[nch];
+  for (size_t c = 0; c < nch; c++) {
+    size_t first = c * PAIRING_CHUNK, np = k - first < (size_t)PAIRING_CHUNK ? k - first : PAIRING_CHUNK;
+    Fp12 f; fp12_set_one(f);
+    bool started = false;
+    int s = 0;
+    for (int i = 62; i >= 0; i--) {
+      if (started) fp12_sqr(f, f);
+      int nsteps = ((B200_Z_ABS >> i) & 1) ? 2 : 1;
+      for (int a = 0; a < nsteps; a++, s++)
+        for (size_t q = 0; q < np; q++) {
+          size_t j = first + q;
+          if (skip[j]) continue;
+          const Line& ln = lines[s * k + j];
+          fp12_mul_by_014(f, ln.l0, ln.l1, ln.l4);
+          started = true;
+        }
+    }
+    fp12_conj(f, f);
+    fch[c] = f;
+  }
+  counts[2] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  Fp12 acc = fch[0];
+  for (size_t c = 1; c < nch; c++) fp12_mul(acc, acc, fch[c]);
+  final_exp(acc, acc);
+  counts[3] = g_fp_mul_count - c0;
+  memset(out32, 0, 32);
+  if (fp12_is_one(acc)) out32[31] = 1;
+  delete[] ps; delete[] qs; delete[] lines; delete[] skip; delete[] fch;
+  return 0;
+}
+// Fp multiplications of one XYZZ mixed addition / full addition / doubling over Fp and Fp2
+void emul_point_op_fme(unsigned long long* c6, const unsigned char* g1_128, const unsigned char* g2_256) {
+  uint32_t w[64];
+  load_words(w, g1_128, 32); G1Affine p; decode_point(p, w);
+  load_words(w, g2_256, 64); G2Affine q; decode_point(q, w);
+  G1XYZZ a = xyzz_dbl_affine(p); G2XYZZ b = xyzz_dbl_affine(q);
+  unsigned long long c0 = g_fp_mul_count;
+  xyzz_madd(a, p); c6[0] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  { G1XYZZ t = xyzz_dbl(a); xyzz_add(a, t); } c6[1] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  a = xyzz_dbl(a); c6[2] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  xyzz_madd(b, q); c6[3] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  { G2XYZZ t = xyzz_dbl(b); xyzz_add(b, t); } c6[4] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
+  b = xyzz_dbl(b); c6[5] = g_fp_mul_count - c0;
 }
 int emul_g1_in_subgroup(const unsigned char* in128) {
   uint32_t w[32]; load_words(w, in128, 32);

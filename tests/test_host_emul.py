@@ -107,3 +107,20 @@ def test_subgroup_checks(emul, oracle_c):
         if y * y % o.P == (x ** 3 + 4) % o.P:
             assert emul.emul_g1_in_subgroup(o.encode_g1((x, y))) == 0
             n += 1
+
+
+def test_pairing_fme_constants(emul, oracle_c):
+    """bench.py's roofline for the pairing batch uses these per-pair / per-chunk / per-call Fp-mul counts."""
+    import workloads as wl
+    rng = wl.SplitMix64(5)
+    for k in (2, 3, 4, 9):
+        data = wl.pairing_call(k, rng, True)
+        c = (ctypes.c_ulonglong * 4)()
+        out = ctypes.create_string_buffer(32)
+        assert emul.emul_pairing_fme_counts(c, out, data, ctypes.c_size_t(k)) == 0
+        nch = (k + 2) // 3
+        assert list(c) == [2986 * k, 2221 * k, 2652 * k + 2232 * nch, 7688 + 54 * (nch - 1)]
+        assert out.raw == oracle_c.call("pairing", data)[1]
+    c6 = (ctypes.c_ulonglong * 6)()
+    emul.emul_point_op_fme(c6, o.encode_g1(o.G1), o.encode_g2(o.G2))
+    assert list(c6) == [10, 23, 9, 28, 64, 24]     # madd, dbl+add, dbl over Fp / Fp2 (SURVEY.md 8d)
