@@ -296,7 +296,7 @@ __device__ __forceinline__ void accumulate_segment(XYZZ<F>& acc, const Affine<F>
 
 // one thread per bucket, buckets taken in order of decreasing size; at most `cap` entries each
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(128, 4) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                     const uint32_t* __restrict__ order, uint32_t nbuckets_total, uint32_t cap,
                                                     int add_to_existing, XYZZ<F>* __restrict__ buckets) {
