@@ -127,3 +127,21 @@ def launch_count() -> int:
 
 def set_window(c: int) -> None:
     _native.lib().bls12_b200_set_window(int(c))
+
+
+def points_check(group: int, data, stride: int = 0, check_subgroup: bool = True):
+    """Batched validation of encoded points -> int32 codes (0 ok, 3 invalid element, 1 off curve, 2 not in subgroup)."""
+    ptr, nbytes, keep = _buf(data)
+    stride = stride or (128 if group == 1 else 256)
+    assert nbytes % stride == 0 and stride % 16 == 0
+    n = nbytes // stride
+    codes = np.zeros(n, dtype=np.int32)
+    code = _native.lib().bls12_b200_points_check(group, ptr, n, stride, 1 if check_subgroup else 0, codes.ctypes.data)
+    del keep
+    if code != SUCCESS:
+        raise EIP2537Error(code)
+    return codes
+
+
+def set_checked_msm(on: bool) -> None:
+    _native.lib().bls12_b200_set_checked_msm(1 if on else 0)

@@ -26,6 +26,7 @@ using namespace b200;
 static std::atomic<uint64_t> g_launches{0};
 static thread_local char g_last_error[256] = "";
 static std::atomic<int> g_forced_window{0};
+static std::atomic<int> g_checked_msm{0};   // opt-in: subgroup-check MULTIEXP inputs (changes error codes vs the reference)
 
 #define CUDA_TRY(expr)                                                                          \
   do {                                                                                          \
@@ -209,12 +210,17 @@ static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
 template <class F>
 static int msm_feed(Engine& e, MsmRun<F>& r, const uint32_t* d_raw, size_t n, uint64_t index_base, bool first,
                     unsigned long long* d_status, cudaStream_t s) {
-  (void)e;
   const MsmPlan& plan = r.plan;
   const size_t nbt = r.nbt;
   if (first) g_stage.mark(0, s);
   CUDA_TRY(cudaMemsetAsync(r.counts, 0, 2 * nbt * sizeof(uint32_t), s));
   LAUNCH(k_decode<F>, blocks_for(n, 128), 128, s, d_raw, n, r.pts, d_status, (size_t)index_base);
+  if (g_checked_msm.load()) {   // opt-in "checked MSM" (SURVEY.md 8(f)-4): reject points outside G1/G2 with code 2
+    int rc2 = e.pr_status.reserve(n * sizeof(int));
+    if (rc2) return rc2;
+    LAUNCH(k_points_check<F>, blocks_for(n, 64), 64, s, d_raw, n, Wire<F>::PAIR_WORDS, 1, (int*)e.pr_status.ptr);
+    LAUNCH(k_codes_to_status, blocks_for(n, 256), 256, s, (const int*)e.pr_status.ptr, n, (size_t)index_base, d_status);
+  }
   LAUNCH(k_digits<F>, blocks_for(n, 256), 256, s, d_raw, n, r.pts, plan, r.digits, r.counts);
   unsigned nblk = blocks_for(nbt, 1024);
   LAUNCH(k_scan_blocks, nblk, 1024, s, r.counts, r.offsets, r.block_sums, (uint32_t)nbt);
@@ -806,6 +812,40 @@ extern "C" void bls12_b200_shutdown(void) {
 extern "C" const char* bls12_b200_last_error(void) { return g_last_error; }
 extern "C" uint64_t bls12_b200_launch_count(void) { return g_launches.load(); }
 extern "C" void bls12_b200_set_window(int c) { g_forced_window.store(c); }
+extern "C" void bls12_b200_set_checked_msm(int on) { g_checked_msm.store(on); }
+
+// batched point validation: device-resident and host-buffer forms
+extern "C" EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d_points, size_t n, size_t stride_bytes,
+                                                        int check_subgroup, int32_t* d_codes, void* stream) {
+  if (n == 0) return EIP2537_SUCCESS;
+  if (((uintptr_t)d_points & 15) || (stride_bytes & 15)) {
+    snprintf(g_last_error, sizeof g_last_error, "points and stride must be 16-byte aligned");
+    return EIP2537_MEMORY_ERROR;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (group == 1) LAUNCH(k_points_check<Fp>, blocks_for(n, 64), 64, s, (const uint32_t*)d_points, n, (int)(stride_bytes / 4), check_subgroup, (int*)d_codes);
+  else            LAUNCH(k_points_check<Fp2>, blocks_for(n, 64), 64, s, (const uint32_t*)d_points, n, (int)(stride_bytes / 4), check_subgroup, (int*)d_codes);
+  CUDA_TRY2(cudaGetLastError());
+  return EIP2537_SUCCESS;
+}
+extern "C" EIP2537_ERROR bls12_b200_points_check(int group, const byte* points, size_t n, size_t stride_bytes,
+                                                 int check_subgroup, int32_t* codes) {
+  if (n == 0) return EIP2537_SUCCESS;
+  Engine* ep;
+  int rc = engine_get(&ep, -1);
+  if (rc) return (EIP2537_ERROR)rc;
+  Engine& e = *ep;
+  std::lock_guard<std::mutex> lk(e.mu);
+  const size_t bytes = n * stride_bytes;
+  if ((rc = e.raw.reserve(bytes)) || (rc = e.pr_status.reserve(n * sizeof(int)))) return (EIP2537_ERROR)rc;
+  cudaStream_t s = e.stream;
+  CUDA_TRY2(cudaMemcpyAsync(e.raw.ptr, points, bytes, cudaMemcpyHostToDevice, s));
+  EIP2537_ERROR r = bls12_b200_points_check_device(group, e.raw.ptr, n, stride_bytes, check_subgroup, (int32_t*)e.pr_status.ptr, (void*)s);
+  if (r) return r;
+  CUDA_TRY2(cudaMemcpyAsync(codes, e.pr_status.ptr, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY2(cudaStreamSynchronize(s));
+  return EIP2537_SUCCESS;
+}
 // stage_ms4 = {decode + subgroup checks, line functions, chunked accumulate, product + final exp}
 extern "C" EIP2537_ERROR bls12_b200_last_pairing_profile(float* stage_ms4) {
   if (g_pstage.used < 5) return EIP2537_EMPTY_INPUT;

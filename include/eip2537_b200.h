@@ -59,6 +59,20 @@ EIP2537_ERROR bls12_b200_msm_combine_device(int group, const void* d_partials, i
 EIP2537_ERROR bls12_b200_pairing_batch_device(const void* d_in, const uint64_t* d_offsets, size_t n,
                                               size_t total_pairs, void* d_outs, int32_t* d_errs, void* stream);
 
+/* ---- batched point validation (K3).  points: n encoded points, `stride_bytes` apart (128 / 256 for bare
+ *      point arrays, 160 / 288 to walk a MULTIEXP input, 384 for the G1 fields of a PAIRING input;
+ *      a multiple of 16).  codes[i] = 0, EIP2537_INVALID_ELEMENT, EIP2537_POINT_NOT_ON_CURVE, or --
+ *      when check_subgroup != 0 -- EIP2537_POINT_NOT_IN_SUBGROUP (the test the reference applies in
+ *      PAIRING, src/eip2537.c:1041/:1051). */
+EIP2537_ERROR bls12_b200_points_check(int group, const byte* points, size_t n, size_t stride_bytes,
+                                      int check_subgroup, int32_t* codes);
+EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d_points, size_t n, size_t stride_bytes,
+                                             int check_subgroup, int32_t* d_codes, void* stream);
+/* opt-in "checked MSM": MULTIEXP additionally rejects points outside G1/G2 with
+ * EIP2537_POINT_NOT_IN_SUBGROUP.  OFF by default because the reference does not check
+ * (src/eip2537.c:340, :401 are TODOs) and the codes would differ. */
+void bls12_b200_set_checked_msm(int on);
+
 /* ---- workload generators (synthetic inputs): out[i] = encode(k_i * generator),
  *      k_i = 32-byte big-endian scalars.  Host buffers. */
 EIP2537_ERROR bls12_b200_g1_generator_mul(byte* out, const byte* scalars, size_t n);

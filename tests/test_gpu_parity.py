@@ -252,3 +252,41 @@ def test_g2_subgroup_rejection_in_pairing(product, oracle_c):
     assert product.raw_call("bls12_pairing", G1B + q, 32)[0] == 2
     # ... but it is a legal MULTIEXP input
     assert product.G2Multiexp(q + ONES) == oracle_c.call("g2multiexp", q + ONES)[1]
+
+
+def test_batched_point_validation(product, oracle_c):
+    """K3 as a standalone batch: per-point codes incl. the subgroup test, against the oracle's fast and naive tests."""
+    rnd = random.Random(21)
+    pts = [G1B, bytes(128), po.encode_g1((0, 2)), G1B[:64] + po.fp_to_bytes(5), bytes(16) + po.P.to_bytes(48, "big") + G1B[64:]]
+    while len(pts) < 40:
+        x = rnd.randrange(po.P)
+        y = pow((x ** 3 + 4) % po.P, (po.P + 1) // 4, po.P)
+        if y * y % po.P == (x ** 3 + 4) % po.P:
+            pts.append(po.encode_g1((x, y)))                      # on curve, outside G1
+        pts.append(oracle_c.g1_gen_mul(rnd.randrange(po.R)))      # in G1
+    codes = product.points_check(1, b"".join(pts))
+    want = []
+    for p in pts:
+        err, _ = oracle_c.call("g1mul", p + bytes(32))
+        if err == 0 and oracle_c.lib().oracle_g1_in_subgroup(p, 1) != 1:
+            err = 2
+        want.append(err)
+    assert list(codes) == want
+    assert list(product.points_check(1, b"".join(pts), check_subgroup=False)) == [0 if w == 2 else w for w in want]
+    q = [G2B, bytes(256), G2B[:192] + po.fp_to_bytes(7), oracle_c.g2_gen_mul(12345)]
+    assert list(product.points_check(2, b"".join(q))) == [0, 0, 1, 0]
+
+
+def test_checked_msm_opt_in(product, oracle_c):
+    """Off by default (reference semantics); when enabled, non-subgroup points give code 2."""
+    order3 = po.encode_g1((0, 2))
+    data = G1B + ONES + order3 + ONES
+    assert product.raw_call("bls12_g1multiexp", data, 128)[0] == 0
+    product.set_checked_msm(True)
+    try:
+        assert product.raw_call("bls12_g1multiexp", data, 128)[0] == 2
+        ok = G1B + ONES + oracle_c.g1_gen_mul(77) + ONES
+        assert product.G1Multiexp(ok) == oracle_c.call("g1multiexp", ok)[1]
+    finally:
+        product.set_checked_msm(False)
+    assert product.raw_call("bls12_g1multiexp", data, 128)[0] == 0

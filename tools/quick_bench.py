@@ -74,3 +74,18 @@ if "pairing" in what:
         t0 = time.time(); outs, errs = b.PairingBatch(blob, o); dt = time.time() - t0
     assert [int(x[31]) for x in outs[:64]] == [1 if t else 0 for t in truth] and not errs.any()
     print("pairing batch %d calls (%d pairs): %.1f ms -> %.0f checks/s" % (len(o) - 1, len(blob) // 384, dt * 1e3, (len(o) - 1) / dt), flush=True)
+
+if "check" in what:
+    n = 1 << 20
+    data = gen_g1(n)
+    d_in = torch.from_numpy(data).cuda()
+    d_codes = torch.zeros(n, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for sub in (0, 1):
+        for rep in range(3):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            assert L.bls12_b200_points_check_device(1, d_in.data_ptr(), n, 160, sub, d_codes.data_ptr(), s) == 0
+            ev1.record(); torch.cuda.synchronize()
+        assert int(d_codes.abs().sum().item()) == 0
+        print("G1 batched decode%s over a 2^20-pair MULTIEXP input: %.3f ms -> %.3e points/s" % (" + subgroup check" if sub else "", ev0.elapsed_time(ev1), n / (ev0.elapsed_time(ev1) * 1e-3)), flush=True)
