@@ -162,6 +162,62 @@ B200_HD_NI XYZZ<F> xyzz_scalar_mul(const Affine<F>& p, const uint32_t* k, int nb
   return acc;
 }
 
+// ---- Jacobian coordinates (x = X/Z^2, y = Y/Z^3), used where doublings dominate: the fixed-scalar
+// multiplications of the subgroup checks.  dbl-2009-l costs 2M+5S (XYZZ: 6M+3S), madd-2007-bl 7M+4S.
+template <class F>
+struct Jac {     // infinity <=> z == 0
+  F x, y, z;
+};
+template <class F>
+B200_HD_NI void jac_dbl(Jac<F>& p) {
+  if (is_zero(p.z)) return;
+  F a = sqr(p.x), b = sqr(p.y), c = sqr(b);
+  F d = dbl(sub(sub(sqr(add(p.x, b)), a), c));
+  F e = add(dbl(a), a);
+  F f = sqr(e);
+  F z3 = dbl(mul(p.y, p.z));
+  F x3 = sub(f, dbl(d));
+  F c8 = dbl(dbl(dbl(c)));
+  p.y = sub(mul(e, sub(d, x3)), c8);
+  p.x = x3;
+  p.z = z3;
+}
+// p += q, q affine and finite; complete (p infinite, p == q, p == -q handled exactly)
+template <class F>
+B200_HD_NI void jac_madd(Jac<F>& p, const Affine<F>& q) {
+  if (is_zero(p.z)) { p.x = q.x; p.y = q.y; p.z = FieldOps<F>::one(); return; }
+  F z1z1 = sqr(p.z);
+  F u2 = mul(q.x, z1z1);
+  F s2 = mul(mul(q.y, p.z), z1z1);
+  F h = sub(u2, p.x);
+  F r = sub(s2, p.y);
+  if (is_zero(h)) {
+    if (is_zero(r)) { p.x = q.x; p.y = q.y; p.z = FieldOps<F>::one(); jac_dbl(p); }
+    else            { p.x = FieldOps<F>::zero(); p.y = FieldOps<F>::zero(); p.z = FieldOps<F>::zero(); }
+    return;
+  }
+  r = dbl(r);
+  F hh = sqr(h);
+  F i = dbl(dbl(hh));
+  F j = mul(h, i);
+  F v = mul(p.x, i);
+  F x3 = sub(sub(sqr(r), j), dbl(v));
+  F y3 = sub(mul(r, sub(v, x3)), dbl(mul(p.y, j)));
+  F z3 = sub(sub(sqr(add(p.z, h)), z1z1), hh);
+  p.x = x3; p.y = y3; p.z = z3;
+}
+// k * P for a finite affine P, k = `nbits` significant bits of little-endian words
+template <class F>
+B200_HD_NI Jac<F> jac_scalar_mul(const Affine<F>& p, const uint32_t* k, int nbits) {
+  Jac<F> acc;
+  acc.x = FieldOps<F>::zero(); acc.y = FieldOps<F>::zero(); acc.z = FieldOps<F>::zero();
+  for (int i = nbits - 1; i >= 0; i--) {
+    jac_dbl(acc);
+    if ((k[i >> 5] >> (i & 31)) & 1) jac_madd(acc, p);
+  }
+  return acc;
+}
+
 using G1Affine = Affine<Fp>;
 using G2Affine = Affine<Fp2>;
 using G1XYZZ = XYZZ<Fp>;

@@ -231,20 +231,22 @@ B200_HD_NI void final_exp(Fp12& r, const Fp12& fin) {
 B200_HD_NI bool g1_in_subgroup(const G1Affine& p) {
   if (is_inf(p)) return true;
   const uint32_t zsq[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};   // z^2, little-endian words
-  G1XYZZ q = xyzz_scalar_mul(p, zsq, 128);
-  if (is_inf(q)) return false;
-  // compare phi(P) with -q without leaving XYZZ: beta*x*ZZ == X and  y*ZZZ == -Y
+  Jac<Fp> q = jac_scalar_mul(p, zsq, 128);
+  if (is_zero(q.z)) return false;
+  // phi(P) == -q  without leaving Jacobian coordinates:  beta*x*Z^2 == X  and  y*Z^3 == -Y
+  Fp z2 = sqr(q.z);
   Fp bx = mul(p.x, fp_load_const(C_BETA()));
-  return eq(mul(bx, q.zz), q.x) && eq(mul(p.y, q.zzz), neg(q.y));
+  return eq(mul(bx, z2), q.x) && eq(mul(p.y, mul(z2, q.z)), neg(q.y));
 }
 B200_HD_NI bool g2_in_subgroup(const G2Affine& p) {
   if (is_inf(p)) return true;
   const uint32_t zabs[2] = {(uint32_t)(B200_Z_ABS & 0xffffffffu), (uint32_t)(B200_Z_ABS >> 32)};
-  G2XYZZ q = xyzz_scalar_mul(p, zabs, 64);
-  if (is_inf(q)) return false;
+  Jac<Fp2> q = jac_scalar_mul(p, zabs, 64);
+  if (is_zero(q.z)) return false;
+  Fp2 z2 = sqro(q.z);
   Fp2 px = mulo(conj(p.x), fp2_load_const(C_PSI_CX()));
   Fp2 py = mulo(conj(p.y), fp2_load_const(C_PSI_CY()));
-  return eq(mulo(px, q.zz), q.x) && eq(mulo(py, q.zzz), neg(q.y));   // [z]Q = -[|z|]Q
+  return eq(mulo(px, z2), q.x) && eq(mulo(py, mulo(z2, q.z)), neg(q.y));   // [z]Q = -[|z|]Q
 }
 
 static constexpr int PAIRING_CHUNK = 3;
