@@ -470,11 +470,11 @@ def run_ours(args, rank, world, local_rank):
         if args.workload == "pairing" and rank == 0:
             # Fp-multiplication counts of the GPU's own formulas, measured with the host-emulation build
             # (tests/test_host_emul.py::test_pairing_fme_constants pins them): per pair 2256 (decode + G1/G2
-            # subgroup checks) + 2221 (68 line functions) + 2652 (68 sparse Fp12 products); per chunk of <= 3
+            # subgroup checks) + 1780 (68 line functions) + 2652 (68 sparse Fp12 products); per chunk of <= 3
             # pairs 2232 (62 Fp12 squarings); per call 7688 (final exponentiation) + 54 per extra chunk.
             ks = [2 + ((rank * calls + j) % 15) for j in range(calls)]
             nch = [(k + 2) // 3 for k in ks]
-            fme = {"decode": DECODE_FME * sum(ks), "lines": 2221 * sum(ks), "accumulate": 2652 * sum(ks) + 2232 * sum(nch),
+            fme = {"decode": DECODE_FME * sum(ks), "lines": 1780 * sum(ks), "accumulate": 2652 * sum(ks) + 2232 * sum(nch),
                    "calls": sum(7688 + 54 * (c - 1) for c in nch)}
             L.bls12_b200_set_profile(1)
             st = (ctypes.c_float * 4)()

@@ -192,6 +192,24 @@ B200_HD Fp sub(const Fp& a, const Fp& b) {
 }
 B200_HD Fp neg(const Fp& a) { return sub(fp_zero(), a); }
 B200_HD Fp dbl(const Fp& a) { return add(a, a); }
+// a/2 mod p: add p when odd, shift right (works in Montgomery form as well: halving commutes with *R)
+B200_HD Fp half(const Fp& a) {
+  const uint32_t* p = C_P();
+  const uint32_t mask = 0u - (a.v[0] & 1u);
+  uint32_t t[13];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    uint64_t s = (uint64_t)a.v[i] + (p[i] & mask) + c;
+    t[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  t[12] = (uint32_t)c;
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------
 // Montgomery multiplication  r = a*b/2^384 mod p
@@ -449,6 +467,7 @@ B200_HD_NI Fp2 sqr(const Fp2& a) {
   return r;
 }
 B200_HD_NI Fp2 mul_fp(const Fp2& a, const Fp& k) { Fp2 r; r.c0 = mul(a.c0, k); r.c1 = mul(a.c1, k); return r; }
+B200_HD Fp2 half(const Fp2& a) { Fp2 r; r.c0 = half(a.c0); r.c1 = half(a.c1); return r; }
 B200_HD Fp2 mul_xi(const Fp2& a) { Fp2 r; r.c0 = sub(a.c0, a.c1); r.c1 = add(a.c0, a.c1); return r; }
 B200_HD Fp2 inv(const Fp2& a) {
   Fp t = inv(add(sqr(a.c0), sqr(a.c1)));

@@ -154,12 +154,13 @@ B200_HD_NI void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
 struct G2Proj { Fp2 x, y, z; };   // homogeneous projective point on the twist
 
 B200_HD_NI void ml_dbl_step(G2Proj& t, Fp2& l0, Fp2& l1, Fp2& l4) {
-  const Fp inv2 = fp_load_const(C_INV2());
-  Fp2 a = mulfpo(mulo(t.x, t.y), inv2);
+  Fp2 a = half(mulo(t.x, t.y));
   Fp2 b = sqro(t.y), c = sqro(t.z);
-  Fp2 e = mulo(fp2_load_const(C_B2X3()), c);
+  // e = 3b' * c with 3b' = 12(1+u): multiplication by xi, then 12x by doublings (no field multiplication)
+  Fp2 c4 = dbl(dbl(mul_xi(c)));
+  Fp2 e = add(dbl(c4), c4);
   Fp2 f = add(dbl(e), e);
-  Fp2 g = mulfpo(add(b, f), inv2);
+  Fp2 g = half(add(b, f));
   Fp2 h = sub(sqro(add(t.y, t.z)), add(b, c));
   Fp2 j = sqro(t.x);
   Fp2 e2 = sqro(e);
