@@ -517,16 +517,21 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   PairingTask* tasks = (PairingTask*)(ntasks + 16);
   uint32_t* call_first = (uint32_t*)(tasks + max_tasks);
   Fp12* f = (Fp12*)e.pr_f.ptr;
+  // Pairs per chunk.  3 measured best for the 16384-call batch (2 waves of 168-register threads); larger
+  // chunks share more squarings but lengthen each thread's serial chain (4: 46 ms, 5: 46 ms vs 35 ms), and
+  // limiting residency so the thread-local Fp12 scratch fits the L2 did not pay either (38 ms).
+  static const int forced_chunk = getenv("B200_PAIRING_CHUNK") ? atoi(getenv("B200_PAIRING_CHUNK")) : 0;
+  uint32_t chunk = forced_chunk > 0 ? (uint32_t)forced_chunk : (uint32_t)PAIRING_CHUNK;
   CUDA_TRY(cudaMemsetAsync(ntasks, 0, 64, s));
   g_pstage.mark(0, s);
   LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
   g_pstage.mark(1, s);
   LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
   g_pstage.mark(2, s);
-  LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, ntasks, tasks, call_first, d_errs);
+  LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, chunk, ntasks, tasks, call_first, d_errs);
   LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, ntasks, lines, skip, total_pairs, f);
   g_pstage.mark(3, s);
-  LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, call_first, f, d_outs, d_errs);
+  LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, chunk, call_first, f, d_outs, d_errs);
   g_pstage.mark(4, s);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;

@@ -250,7 +250,7 @@ B200_HD_NI bool g2_in_subgroup(const G2Affine& p) {
   return eq(mulo(px, z2), q.x) && eq(mulo(py, mulo(z2, q.z)), neg(q.y));   // [z]Q = -[|z|]Q
 }
 
-static constexpr int PAIRING_CHUNK = 3;
+static constexpr int PAIRING_CHUNK = 3;       // default pairs per chunk (the engine adapts it to the batch)
 static constexpr int ML_STEPS = 68;          // 63 doubling steps + 5 addition steps (|z| has weight 6)
 
 struct Line { Fp2 l0, l1, l4; };             // l0 + l1*w^2 + l4*w^3, already multiplied by xP / yP
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(64, 6) k_pairing_lines(const G1Affine* __restr
 // one thread per call: decide the call's error code (first failing pair, eip2537.c:1033-1053) and cut
 // the call into chunks for k_pairing_accumulate
 __global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* __restrict__ offsets, size_t n_calls,
-                                                      const int* __restrict__ status, uint32_t* ntasks,
+                                                      const int* __restrict__ status, uint32_t chunk, uint32_t* ntasks,
                                                       PairingTask* __restrict__ tasks, uint32_t* __restrict__ call_first_task,
                                                       int* __restrict__ errs) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,11 +374,11 @@ __global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* 
   for (size_t j = first; j < last; j++)
     if (status[j] != E_SUCCESS) { errs[i] = status[j]; return; }
   errs[i] = E_SUCCESS;
-  uint32_t k = (uint32_t)(last - first), nch = (k + PAIRING_CHUNK - 1) / PAIRING_CHUNK;
+  uint32_t k = (uint32_t)(last - first), nch = (k + chunk - 1) / chunk;
   uint32_t base = atomicAdd(ntasks, nch);
   call_first_task[i] = base;
   for (uint32_t c = 0; c < nch; c++) {
-    uint32_t lo = c * PAIRING_CHUNK, len = k - lo < PAIRING_CHUNK ? k - lo : PAIRING_CHUNK;
+    uint32_t lo = c * chunk, len = k - lo < chunk ? k - lo : chunk;
     tasks[base + c] = PairingTask{(uint32_t)first + lo, len};
   }
 }
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(64, 6) k_pairing_accumulate(const PairingTask*
 
 // one thread per call: product of the chunks' Miller values (blst_fp12_mul, :1061), one final
 // exponentiation (:1070), is-one -> out[31] (:1076)
-__global__ void __launch_bounds__(64) k_pairing_calls(size_t n_calls, const unsigned long long* __restrict__ offsets,
+__global__ void __launch_bounds__(64) k_pairing_calls(size_t n_calls, const unsigned long long* __restrict__ offsets, uint32_t chunk,
                                                       const uint32_t* __restrict__ call_first_task, const Fp12* __restrict__ fchunk,
                                                       uint32_t* __restrict__ outs, const int* __restrict__ errs) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(64) k_pairing_calls(size_t n_calls, const unsi
   uint32_t* out = outs + 8 * i;
   for (int k = 0; k < 8; k++) out[k] = 0;
   if (errs[i] != E_SUCCESS) return;
-  uint32_t npairs = (uint32_t)(offsets[i + 1] / 384 - offsets[i] / 384), nch = (npairs + PAIRING_CHUNK - 1) / PAIRING_CHUNK;
+  uint32_t npairs = (uint32_t)(offsets[i + 1] / 384 - offsets[i] / 384), nch = (npairs + chunk - 1) / chunk;
   uint32_t base = call_first_task[i];
   Fp12 acc = fchunk[base], cur;
   for (uint32_t c = 1; c < nch; c++) {
