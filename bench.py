@@ -340,8 +340,14 @@ def run_ours(args, rank, world, local_rank):
             def step_e2e():
                 if world == 1:
                     return b.G1Multiexp(h_in) if group == 1 else b.G2Multiexp(h_in)
-                d_in.copy_(h_in, non_blocking=True)
-                step_device()
+                # host-resident shard streamed through the C ABI, then the same exchange + combine
+                rc = L.bls12_b200_msm_partial_host(group, h_in.data_ptr(), n, rank * n, d_partial.data_ptr(), d_status.data_ptr())
+                assert rc == 0, L.bls12_b200_last_error()
+                dist.all_gather_into_tensor(d_gather, d_partial)
+                d_status.copy_(torch.where(d_status < 0, torch.iinfo(torch.int64).max, d_status))
+                dist.all_reduce(d_status, op=dist.ReduceOp.MIN)
+                d_status.copy_(torch.where(d_status == torch.iinfo(torch.int64).max, -1, d_status))
+                assert L.bls12_b200_msm_combine_device(group, d_gather.data_ptr(), world, d_out.data_ptr(), s) == 0
                 return bytes(d_out.cpu().numpy())
 
             units_per_step = n * world

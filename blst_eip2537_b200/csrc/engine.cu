@@ -299,22 +299,15 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
   return msm_tail<F>(e, r, d_partial, s);
 }
 
-// host-resident input: stream it in chunks, copy of chunk i+1 overlapped with accumulation of chunk i
+// host-resident input: stream it in chunks, copy of chunk i+1 overlapped with accumulation of chunk i.
+// Leaves the XYZZ partial sum in e.partial and the status key in e.status (both on the device), all work
+// queued on e.stream.
 template <class F>
-static int msm_host_impl(const unsigned char* in, size_t n, unsigned char* out) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
-  if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
-  int prev;
-  CUDA_TRY(cudaGetDevice(&prev));
-  if (prev != e.device) CUDA_TRY(cudaSetDevice(e.device));
-  const size_t pair_bytes = Wire<F>::PAIR_WORDS * 4, out_bytes = Wire<F>::POINT_WORDS * 4;
-  const size_t in_bytes = n * pair_bytes;
-  if ((rc = e.raw.reserve(in_bytes))) return rc;
-  if ((rc = e.partial.reserve(sizeof(XYZZ<F>)))) return rc;
-  if ((rc = e.out.reserve(out_bytes))) return rc;
+static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, uint64_t index_base) {
+  int rc;
+  const size_t pair_bytes = Wire<F>::PAIR_WORDS * 4;
+  if ((rc = e.raw.reserve(n * pair_bytes))) return rc;
+  if ((rc = e.partial.reserve(sizeof(XYZZ<Fp2>)))) return rc;
   if ((rc = e.status.reserve(8))) return rc;
   cudaStream_t s = e.stream, cs = e.stream2;
   const int nchunks = n >= (1u << 18) ? 8 : (n >= (1u << 16) ? 4 : 1);
@@ -333,9 +326,25 @@ static int msm_host_impl(const unsigned char* in, size_t n, unsigned char* out) 
       CUDA_TRY(cudaEventRecord(e.ev_group[c], cs));
       CUDA_TRY(cudaStreamWaitEvent(s, e.ev_group[c], 0));
     }
-    if ((rc = msm_feed<F>(e, r, (const uint32_t*)dst, hi - lo, lo, c == 0, (unsigned long long*)e.status.ptr, s))) return rc;
+    if ((rc = msm_feed<F>(e, r, (const uint32_t*)dst, hi - lo, index_base + lo, c == 0, (unsigned long long*)e.status.ptr, s))) return rc;
   }
-  if ((rc = msm_tail<F>(e, r, (XYZZ<F>*)e.partial.ptr, s))) return rc;
+  return msm_tail<F>(e, r, (XYZZ<F>*)e.partial.ptr, s);
+}
+
+template <class F>
+static int msm_host_impl(const unsigned char* in, size_t n, unsigned char* out) {
+  Engine* ep;
+  int rc = engine_get(&ep, -1);
+  if (rc) return rc;
+  Engine& e = *ep;
+  std::lock_guard<std::mutex> lk(e.mu);
+  int prev;
+  CUDA_TRY(cudaGetDevice(&prev));
+  if (prev != e.device) CUDA_TRY(cudaSetDevice(e.device));
+  const size_t out_bytes = Wire<F>::POINT_WORDS * 4;
+  if ((rc = e.out.reserve(out_bytes))) return rc;
+  if ((rc = msm_stream_from_host<F>(e, in, n, 0))) return rc;
+  cudaStream_t s = e.stream;
   LAUNCH(k_finalize<F>, 1, 32, s, (const XYZZ<F>*)e.partial.ptr, 1, (uint32_t*)e.out.ptr);
   CUDA_TRY(cudaMemcpyAsync(e.h_out, e.out.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(e.h_status, e.status.ptr, 8, cudaMemcpyDeviceToHost, s));
@@ -344,6 +353,28 @@ static int msm_host_impl(const unsigned char* in, size_t n, unsigned char* out) 
   if (st != STATUS_OK) return (int)(st & 0xFF);
   memcpy(out, e.h_out, out_bytes);   // `out` is written only on success (eip2537.c:613, :701)
   return E_SUCCESS;
+}
+
+// multi-GPU sharding with host-resident shards: stream this rank's slice in, leave the partial sum and
+// the status key in caller-provided DEVICE buffers (ready for the NCCL all-gather); synchronous
+template <class F>
+static int msm_partial_host_impl(const unsigned char* in, size_t n, uint64_t index_base, void* d_partial, uint64_t* d_status) {
+  Engine* ep;
+  int rc = engine_get(&ep, -1);
+  if (rc) return rc;
+  Engine& e = *ep;
+  std::lock_guard<std::mutex> lk(e.mu);
+  if ((rc = msm_stream_from_host<F>(e, in, n, index_base))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_partial, e.partial.ptr, sizeof(XYZZ<F>), cudaMemcpyDeviceToDevice, e.stream));
+  CUDA_TRY(cudaMemcpyAsync(d_status, e.status.ptr, 8, cudaMemcpyDeviceToDevice, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  return E_SUCCESS;
+}
+extern "C" EIP2537_ERROR bls12_b200_msm_partial_host(int group, const byte* in, size_t n, uint64_t index_base,
+                                                     void* d_partial, uint64_t* d_status) {
+  if (n == 0) return EIP2537_INVALID_LENGTH;
+  return (EIP2537_ERROR)(group == 1 ? msm_partial_host_impl<Fp>(in, n, index_base, d_partial, d_status)
+                                    : msm_partial_host_impl<Fp2>(in, n, index_base, d_partial, d_status));
 }
 
 extern "C" int b200_msm_host(int group, const unsigned char* in, size_t n, unsigned char* out) {

@@ -288,14 +288,6 @@ __global__ void k_codes_to_status(const int* __restrict__ codes, size_t n, size_
   if (codes[i] != E_SUCCESS) atomicMin(status, ((unsigned long long)(index_base + i) << 8) | (unsigned)codes[i]);
 }
 
-// pair_call[j] = index of the call that owns pair j   (offsets are byte offsets, 384 B per pair)
-__global__ void k_pairing_index(const unsigned long long* __restrict__ offsets, size_t n_calls, uint32_t* __restrict__ pair_call) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_calls) return;
-  size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
-  for (size_t j = first; j < last; j++) pair_call[j] = (uint32_t)i;
-}
-
 // one thread per pair: decode + subgroup checks in the reference's order
 // (G1 decode, G1 subgroup, G2 decode, G2 subgroup; eip2537.c:1036-1053); status[j] = first failing code
 __global__ void __launch_bounds__(64, 6) k_pairing_decode(const uint32_t* __restrict__ raw, size_t total_pairs,

@@ -50,6 +50,10 @@ size_t bls12_b200_partial_bytes(int group);
  * index_base is added to pair indices reported in d_status (global index of this shard). */
 EIP2537_ERROR bls12_b200_msm_partial_device(int group, const void* d_in, size_t n, uint64_t index_base,
                                             void* d_partial, uint64_t* d_status, void* stream);
+/* same with a HOST-resident shard (pinned or pageable): the shard is streamed in chunks that accumulate
+ * while the next chunk crosses PCIe; d_partial / d_status are device buffers; returns when they are ready */
+EIP2537_ERROR bls12_b200_msm_partial_host(int group, const byte* in, size_t n, uint64_t index_base,
+                                          void* d_partial, uint64_t* d_status);
 /* sum `count` partials (e.g. after an NCCL all-gather), convert to affine and encode */
 EIP2537_ERROR bls12_b200_msm_combine_device(int group, const void* d_partials, int count, void* d_out,
                                             void* stream);
