@@ -372,6 +372,7 @@ B200_HD Fp mul_portable(const Fp& a, const Fp& b) {
 #if !(defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE))
 B200_HD Fp mul(const Fp& a, const Fp& b) { return mul_portable(a, b); }
 #endif
+
 B200_HD Fp sqr(const Fp& a) { return mul(a, a); }
 
 B200_HD Fp fp_to_mont(const Fp& a) { return mul(a, fp_load_const(C_RR())); }

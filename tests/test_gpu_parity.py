@@ -290,3 +290,32 @@ def test_checked_msm_opt_in(product, oracle_c):
     finally:
         product.set_checked_msm(False)
     assert product.raw_call("bls12_g1multiexp", data, 128)[0] == 0
+
+
+def test_concurrent_callers_share_one_gpu(product, oracle_c):
+    """The reference is re-entrant (no globals); the replacement must be callable from many threads."""
+    import threading
+    jobs = []
+    for n in (3, 50, 700, 9):
+        d, _ = wl.g1_msm_input(n, 0x5151 + n)
+        jobs.append(("g1", d, oracle_c.call("g1multiexp", d)[1]))
+    d2, _ = wl.g2_msm_input(20, 7)
+    jobs.append(("g2", d2, oracle_c.call("g2multiexp", d2)[1]))
+    rng = wl.SplitMix64(9)
+    pd = wl.pairing_call(3, rng, True)
+    jobs.append(("pairing", pd, oracle_c.call("pairing", pd)[1]))
+    results = [None] * (len(jobs) * 3)
+
+    def work(slot, kind, data):
+        fn = {"g1": product.G1Multiexp, "g2": product.G2Multiexp, "pairing": product.Pairing}[kind]
+        results[slot] = fn(data)
+
+    threads = []
+    for rep in range(3):
+        for j, (kind, data, _) in enumerate(jobs):
+            threads.append(threading.Thread(target=work, args=(rep * len(jobs) + j, kind, data)))
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for rep in range(3):
+        for j, (_, _, want) in enumerate(jobs):
+            assert results[rep * len(jobs) + j] == want

@@ -36,6 +36,14 @@ def gen_g1(n):
     return np.concatenate([pts, ks], axis=1).reshape(-1)
 
 
+if "latency" in what:
+    # one warp per SM sub-partition at most: dependent Fp-mul chain latency, CIOS (rolled) vs product scanning
+    for mode, name in ((0, "mul (rolled CIOS)"),):
+        for nthr in (32, 148 * 128, 148 * 2048):
+            iters = 2000
+            L.bls12_b200_fp_microbench(mode, nthr, iters, ctypes.byref(ms), None)
+            print("%s, %d threads: %.3f us per dependent mul, %.3e mul/s" % (name, nthr, ms.value * 1e3 / iters, nthr * iters / (ms.value * 1e-3)), flush=True)
+
 if "msm" in what:
     for logn in (7, 10, 12, 14, 16, 18, 20):
         n = 1 << logn
