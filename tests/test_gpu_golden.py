@@ -93,3 +93,27 @@ def test_pairing_batch_1024_calls_properties(product, oracle_c):
     assert [bool(o[31]) for o in outs] == truth
     for j in (0, 3, 14, 255):
         assert oracle_c.call("pairing", data[offs[j]:offs[j + 1]]) == (0, bytes(outs[j]))
+
+
+def test_streamed_chunks_uneven_size_and_error_precedence(product, oracle_c):
+    """Host-buffer MULTIEXP streams the input in chunks; sizes that do not divide evenly and errors in
+    different chunks must behave exactly like one sequential pass (first failing pair wins)."""
+    rng = np.random.default_rng(0x77)
+    n = (1 << 16) + 3
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 0] &= 0x3F
+    pts = np.frombuffer(product.generator_mul(1, a), dtype=np.uint8).reshape(n, 128)
+    k = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    data = np.concatenate([pts, k], axis=1).copy()
+    total = sum(int.from_bytes(bytes(x), "big") * int.from_bytes(bytes(y), "big") for x, y in zip(a, k)) % po.R
+    assert product.G1Multiexp(data.reshape(-1)) == oracle_c.g1_gen_mul(total)
+    g = po.encode_g1(po.G1)
+    off_curve = np.frombuffer(g[:64] + po.fp_to_bytes(5), dtype=np.uint8)
+    bad_elem = np.frombuffer(bytes(16) + po.P.to_bytes(48, "big") + g[64:], dtype=np.uint8)
+    d2 = data.copy()
+    d2[60000, :128] = bad_elem      # last chunk: code 3
+    d2[20000, :128] = off_curve     # second chunk: code 1, earlier index -> wins
+    assert product.raw_call("bls12_g1multiexp", d2.reshape(-1), 128)[0] == 1
+    d3 = data.copy()
+    d3[60000, :128] = bad_elem
+    assert product.raw_call("bls12_g1multiexp", d3.reshape(-1), 128)[0] == 3
