@@ -467,6 +467,11 @@ B200_HD_NI Fp2 sqr(const Fp2& a) {
   r.c1 = dbl(m);
   return r;
 }
+// Karatsuba cross terms with the operand sums formed INSIDE the out-of-line function: the callers
+// (Fp6 / Fp12 code) otherwise have to park every sum in thread-local memory just to pass it by reference
+B200_HD_NI Fp2 mul_sum2(const Fp2& a1, const Fp2& a2, const Fp2& b1, const Fp2& b2) { return mul(add(a1, a2), add(b1, b2)); }
+B200_HD_NI Fp2 mul_sum1(const Fp2& a1, const Fp2& a2, const Fp2& b) { return mul(add(a1, a2), b); }
+B200_HD_NI Fp2 sqr_sum(const Fp2& a1, const Fp2& a2) { return sqr(add(a1, a2)); }
 B200_HD_NI Fp2 mul_fp(const Fp2& a, const Fp& k) { Fp2 r; r.c0 = mul(a.c0, k); r.c1 = mul(a.c1, k); return r; }
 B200_HD Fp2 half(const Fp2& a) { Fp2 r; r.c0 = half(a.c0); r.c1 = half(a.c1); return r; }
 B200_HD Fp2 mul_xi(const Fp2& a) { Fp2 r; r.c0 = sub(a.c0, a.c1); r.c1 = add(a.c0, a.c1); return r; }

@@ -36,17 +36,17 @@ B200_HD void fp6_mul_v(Fp6& r, const Fp6& a) {
 }
 B200_HD_NI void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
   Fp2 t0 = mulo(a.c0, b.c0), t1 = mulo(a.c1, b.c1), t2 = mulo(a.c2, b.c2);
-  Fp2 c0 = add(mul_xi(sub(sub(mulo(add(a.c1, a.c2), add(b.c1, b.c2)), t1), t2)), t0);
-  Fp2 c1 = add(sub(sub(mulo(add(a.c0, a.c1), add(b.c0, b.c1)), t0), t1), mul_xi(t2));
-  Fp2 c2 = add(sub(sub(mulo(add(a.c0, a.c2), add(b.c0, b.c2)), t0), t2), t1);
+  Fp2 c0 = add(mul_xi(sub(sub(mul_sum2(a.c1, a.c2, b.c1, b.c2), t1), t2)), t0);
+  Fp2 c1 = add(sub(sub(mul_sum2(a.c0, a.c1, b.c0, b.c1), t0), t1), mul_xi(t2));
+  Fp2 c2 = add(sub(sub(mul_sum2(a.c0, a.c2, b.c0, b.c2), t0), t2), t1);
   r.c0 = c0; r.c1 = c1; r.c2 = c2;
 }
 // a * (b0 + b1 v)
 B200_HD_NI void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
   Fp2 aa = mulo(a.c0, b0), bb = mulo(a.c1, b1);
-  Fp2 c0 = add(mul_xi(sub(mulo(add(a.c1, a.c2), b1), bb)), aa);
-  Fp2 c1 = sub(sub(mulo(add(b0, b1), add(a.c0, a.c1)), aa), bb);
-  Fp2 c2 = add(sub(mulo(add(a.c0, a.c2), b0), aa), bb);
+  Fp2 c0 = add(mul_xi(sub(mul_sum1(a.c1, a.c2, b1), bb)), aa);
+  Fp2 c1 = sub(sub(mul_sum2(b0, b1, a.c0, a.c1), aa), bb);
+  Fp2 c2 = add(sub(mul_sum1(a.c0, a.c2, b0), aa), bb);
   r.c0 = c0; r.c1 = c1; r.c2 = c2;
 }
 // a * (b1 v)
@@ -130,7 +130,7 @@ B200_HD_NI void fp12_frob(Fp12& r, const Fp12& a, int k) {   // k = 1 or 2
 // Granger-Scott squaring in the cyclotomic subgroup
 B200_HD void fp4_sqr(Fp2& r0, Fp2& r1, const Fp2& a, const Fp2& b) {
   Fp2 t0 = sqro(a), t1 = sqro(b);
-  r1 = sub(sub(sqro(add(a, b)), t0), t1);
+  r1 = sub(sub(sqr_sum(a, b), t0), t1);
   r0 = add(mul_xi(t1), t0);
 }
 B200_HD_NI void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
@@ -161,7 +161,7 @@ B200_HD_NI void ml_dbl_step(G2Proj& t, Fp2& l0, Fp2& l1, Fp2& l4) {
   Fp2 e = add(dbl(c4), c4);
   Fp2 f = add(dbl(e), e);
   Fp2 g = half(add(b, f));
-  Fp2 h = sub(sqro(add(t.y, t.z)), add(b, c));
+  Fp2 h = sub(sqr_sum(t.y, t.z), add(b, c));
   Fp2 j = sqro(t.x);
   Fp2 e2 = sqro(e);
   l0 = sub(e, b);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(64, 6) k_pairing_accumulate(const PairingTask*
       for (uint32_t k = 0; k < task.npairs; k++) {
         size_t j = task.first_pair + k;
         if (skip[j]) continue;
-        Line ln = lines[(size_t)s * total_pairs + j];
+        const Line& ln = lines[(size_t)s * total_pairs + j];   // read in place: no thread-local copy
         fp12_mul_by_014(f, ln.l0, ln.l1, ln.l4);
         started = true;
       }
