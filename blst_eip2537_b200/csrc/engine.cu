@@ -262,7 +262,9 @@ template <class F>
 static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s) {
   const MsmPlan& plan = r.plan;
   int rc;
-  int L0_log = plan.log_nb < 4 ? plan.log_nb : 4;
+  static const int leaf_env = getenv("B200_LEAF_LOG") ? atoi(getenv("B200_LEAF_LOG")) : 0;
+  int L0_want = leaf_env > 0 ? leaf_env : (sizeof(F) == sizeof(Fp) ? 3 : 4);   // measured: 8 buckets per leaf for G1, 16 for G2
+  int L0_log = plan.log_nb < L0_want ? plan.log_nb : L0_want;
   size_t nodes_per_win = plan.nb >> L0_log;
   if ((rc = e.nodes_a.reserve((size_t)plan.nwin * nodes_per_win * sizeof(Node<F>)))) return rc;
   if ((rc = e.nodes_b.reserve((size_t)plan.nwin * (nodes_per_win / 2 + 1) * sizeof(Node<F>)))) return rc;
