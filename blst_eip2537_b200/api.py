@@ -107,6 +107,24 @@ def PairingBatch(data, offsets):
     return outs, errs
 
 
+def MultiexpBatch(group: int, data, offsets):
+    """n independent G1 (group 1) / G2 (group 2) MULTIEXP calls in one submission.
+
+    Returns (outs uint8[n, 128 or 256], errs int32[n]); per-call semantics identical to G{1,2}Multiexp().
+    """
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = offs.size - 1
+    outs = np.zeros((n, 128 if group == 1 else 256), dtype=np.uint8)
+    errs = np.zeros(n, dtype=np.int32)
+    ptr, _, keep = _buf(data)
+    fn = _native.lib().bls12_g1multiexp_batch if group == 1 else _native.lib().bls12_g2multiexp_batch
+    code = fn(outs.ctypes.data, errs.ctypes.data, ptr, offs.ctypes.data, n)
+    del keep
+    if code != SUCCESS:
+        raise EIP2537Error(code)
+    return outs, errs
+
+
 def generator_mul(group: int, scalars) -> bytes:
     """out[i] = encode(k_i * generator) for 32-byte big-endian scalars (synthetic workloads)."""
     ptr, n, keep = _buf(scalars)

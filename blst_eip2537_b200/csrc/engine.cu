@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "engine.h"
 #include "msm.cuh"
@@ -433,6 +434,61 @@ extern "C" EIP2537_ERROR bls12_b200_msm_device(int group, const void* d_in, size
   EIP2537_ERROR r = bls12_b200_msm_partial_device(group, d_in, n, 0, ep->partial.ptr, d_status, (void*)s);
   if (r) return r;
   return bls12_b200_msm_combine_device(group, ep->partial.ptr, 1, d_out, (void*)s);
+}
+
+// ------------------------------------------------------------------------------------------
+// batch of independent small MULTIEXP calls (host buffers)
+// ------------------------------------------------------------------------------------------
+template <class F>
+static int msm_batch_impl(unsigned char* outs, int* errs, const unsigned char* in, const uint64_t* offsets, size_t n) {
+  Engine* ep;
+  int rc = engine_get(&ep, -1);
+  if (rc) return rc;
+  Engine& e = *ep;
+  std::lock_guard<std::mutex> lk(e.mu);
+  constexpr size_t PAIR = Wire<F>::PAIR_WORDS * 4, OUT = Wire<F>::POINT_WORDS * 4;
+  // calls with a bad length contribute no pairs (answered INVALID_LENGTH, eip2537.c:543 / :831)
+  std::vector<unsigned long long> off(n + 1);
+  size_t cursor = 0;
+  bool any_bad = false;
+  for (size_t i = 0; i < n; i++) {
+    size_t len = (size_t)(offsets[i + 1] - offsets[i]);
+    off[i] = cursor;
+    if (len == 0 || len % PAIR) any_bad = true; else cursor += len;
+  }
+  off[n] = cursor;
+  const size_t total_pairs = cursor / PAIR;
+  if ((rc = e.raw.reserve(cursor + 16)) || (rc = e.pr_offsets.reserve((n + 1) * 8)) || (rc = e.pr_outs.reserve(n * OUT)) ||
+      (rc = e.pr_errs.reserve(n * 4)) || (rc = e.buckets.reserve(total_pairs * sizeof(XYZZ<F>))) ||
+      (rc = e.pr_status.reserve(total_pairs * sizeof(int) + 16)))
+    return rc;
+  cudaStream_t s = e.stream;
+  if (!any_bad) {
+    CUDA_TRY(cudaMemcpyAsync(e.raw.ptr, in + offsets[0], cursor, cudaMemcpyHostToDevice, s));
+  } else {
+    for (size_t i = 0; i < n; i++) {
+      size_t len = (size_t)(off[i + 1] - off[i]);
+      if (len) CUDA_TRY(cudaMemcpyAsync((char*)e.raw.ptr + off[i], in + offsets[i], len, cudaMemcpyHostToDevice, s));
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(e.pr_offsets.ptr, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (total_pairs)
+    LAUNCH(k_batch_pair_mul<F>, blocks_for(total_pairs, 128), 128, s, (const uint32_t*)e.raw.ptr, total_pairs,
+           (XYZZ<F>*)e.buckets.ptr, (int*)e.pr_status.ptr);
+  LAUNCH(k_batch_call_sum<F>, blocks_for(n * 32, 128), 128, s, (const unsigned long long*)e.pr_offsets.ptr, n,
+         (const XYZZ<F>*)e.buckets.ptr, (const int*)e.pr_status.ptr, (uint32_t*)e.pr_outs.ptr, (int*)e.pr_errs.ptr);
+  CUDA_TRY(cudaMemcpyAsync(outs, e.pr_outs.ptr, n * OUT, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(errs, e.pr_errs.ptr, n * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));   // `off` and the caller's buffers stay alive until here
+  return E_SUCCESS;
+}
+extern "C" EIP2537_ERROR bls12_g1multiexp_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, const uint64_t* offsets, size_t n) {
+  if (n == 0) return EIP2537_SUCCESS;
+  return (EIP2537_ERROR)msm_batch_impl<Fp>(outs, (int*)errs, in, offsets, n);
+}
+extern "C" EIP2537_ERROR bls12_g2multiexp_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, const uint64_t* offsets, size_t n) {
+  if (n == 0) return EIP2537_SUCCESS;
+  return (EIP2537_ERROR)msm_batch_impl<Fp2>(outs, (int*)errs, in, offsets, n);
 }
 
 // ------------------------------------------------------------------------------------------

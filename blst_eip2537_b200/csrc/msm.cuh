@@ -414,5 +414,68 @@ __global__ void k_finalize(const XYZZ<F>* __restrict__ partials, int count, uint
   for (int i = 0; i < Wire<F>::POINT_WORDS; i++) out_words[i] = w[i];
 }
 
+// ------------------------------------------------------------------------------------------ batch of small calls
+// Many independent MULTIEXP calls in one submission (the EVM shape: thousands of calls of a few to a
+// few hundred pairs).  Pippenger's bucket machinery does not pay at this size and its serial tail costs
+// ~2 ms per call; here every PAIR is one thread doing its own 256-bit double-and-add (the reference's
+// naive strategy, eip2537.c:564-616, made data-parallel across all pairs of all calls), then one warp
+// per call adds the per-pair results, converts to affine once and encodes.
+template <class F>
+__global__ void __launch_bounds__(128) k_batch_pair_mul(const uint32_t* __restrict__ raw, size_t total_pairs,
+                                                        XYZZ<F>* __restrict__ partial, int* __restrict__ codes) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total_pairs) return;
+  constexpr int PW = Wire<F>::POINT_WORDS, SW = Wire<F>::PAIR_WORDS;
+  uint32_t w[SW];
+  const uint4* src = reinterpret_cast<const uint4*>(raw + j * SW);
+#pragma unroll
+  for (int k = 0; k < SW / 4; k++) { uint4 q = __ldg(src + k); w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w; }
+  Affine<F> pt;
+  int code = decode_point(pt, w);
+  codes[j] = code;
+  if (code != E_SUCCESS) return;
+  uint32_t k[8];
+  scalar_from_slot(k, w + PW);
+  partial[j] = xyzz_scalar_mul(pt, k, 256);
+}
+// offsets: byte offsets of the calls (multiples of the pair size, validated by the host layer)
+template <class F>
+__global__ void __launch_bounds__(128) k_batch_call_sum(const unsigned long long* __restrict__ offsets, size_t n_calls,
+                                                        const XYZZ<F>* __restrict__ partial, const int* __restrict__ codes,
+                                                        uint32_t* __restrict__ outs, int* __restrict__ errs) {
+  const size_t call = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (call >= n_calls) return;
+  constexpr int PW = Wire<F>::POINT_WORDS, PAIR_BYTES = Wire<F>::PAIR_WORDS * 4;
+  const size_t first = (size_t)(offsets[call] / PAIR_BYTES), last = (size_t)(offsets[call + 1] / PAIR_BYTES);
+  // first failing pair in input order (eip2537.c:580-592)
+  unsigned first_bad = 0xffffffffu;
+  for (size_t j = first + lane; j < last; j += 32)
+    if (codes[j] != E_SUCCESS) { first_bad = (unsigned)(j - first); break; }
+  for (int o = 16; o >= 1; o >>= 1) { unsigned other = __shfl_xor_sync(0xffffffffu, first_bad, o); first_bad = other < first_bad ? other : first_bad; }
+  uint32_t* out = outs + call * PW;
+  if (first == last || first_bad != 0xffffffffu) {
+    if (lane == 0) errs[call] = first == last ? E_INVALID_LENGTH : codes[first + first_bad];
+    for (int i = lane; i < PW; i += 32) out[i] = 0;
+    return;
+  }
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (size_t j = first + lane; j < last; j += 32) { XYZZ<F> p = partial[j]; xyzz_add(acc, p); }
+  for (int o = 16; o >= 1; o >>= 1) {
+    XYZZ<F> other;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&other);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&acc);
+    for (int k = 0; k < (int)(sizeof(XYZZ<F>) / 4); k++) dst[k] = __shfl_down_sync(0xffffffffu, s[k], o);
+    if (lane < o) xyzz_add(acc, other);
+  }
+  if (lane == 0) {
+    Affine<F> a = xyzz_to_affine(acc);
+    uint32_t w[PW];
+    encode_point(w, a);
+    for (int i = 0; i < PW; i++) out[i] = w[i];
+    errs[call] = E_SUCCESS;
+  }
+}
+
 #endif  // __CUDACC__
 }  // namespace b200

@@ -38,6 +38,15 @@ void bls12_b200_set_window(int c);
 EIP2537_ERROR bls12_pairing_batch(byte* outs, EIP2537_ERROR* errs, const byte* in,
                                   const uint64_t* offsets, size_t n);
 
+/* Same for MULTIEXP: n independent calls (the EVM shape: many calls of a few to a few hundred pairs).
+ * outs = n*128 (G1) / n*256 (G2) bytes.  Each pair is multiplied by its own thread (the reference's
+ * naive strategy made data-parallel), so this is the right entry point for MANY SMALL calls; one large
+ * call belongs to bls12_g{1,2}multiexp (Pippenger). */
+EIP2537_ERROR bls12_g1multiexp_batch(byte* outs, EIP2537_ERROR* errs, const byte* in,
+                                     const uint64_t* offsets, size_t n);
+EIP2537_ERROR bls12_g2multiexp_batch(byte* outs, EIP2537_ERROR* errs, const byte* in,
+                                     const uint64_t* offsets, size_t n);
+
 /* ---- device-resident MSM (group = 1 for G1, 2 for G2).
  *  d_in: n pairs in wire format (160*n / 288*n bytes).  d_out: 128 / 256 encoded bytes.
  *  d_status: one uint64; ~0 on success else (first failing pair index << 8) | code.

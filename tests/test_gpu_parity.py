@@ -319,3 +319,35 @@ def test_concurrent_callers_share_one_gpu(product, oracle_c):
     for rep in range(3):
         for j, (_, _, want) in enumerate(jobs):
             assert results[rep * len(jobs) + j] == want
+
+
+def test_multiexp_batch_matches_single_calls(product, oracle_c):
+    """Many small independent MULTIEXP calls in one submission: bytes and codes per call as the single-call ABI."""
+    calls, want = [], []
+    for n in (1, 2, 3, 5, 17, 40, 1, 128):
+        d, _ = wl.g1_msm_input(n, 0x6000 + n)
+        calls.append(d)
+    off_curve = G1B[:64] + po.fp_to_bytes(5)
+    bad = bytes(16) + po.P.to_bytes(48, "big") + G1B[64:]
+    calls += [G1B + ONES + off_curve + ONES + bad + ONES, G1B + ONES + bad + ONES + off_curve + ONES, b"", G1B + ONES[:20],
+              bytes(160) * 3, po.encode_g1((0, 2)) + ONES + G1B + be32(po.R)]
+    offs = [0]
+    for cdata in calls:
+        offs.append(offs[-1] + len(cdata))
+    outs, errs = product.MultiexpBatch(1, b"".join(calls), offs)
+    for i, cdata in enumerate(calls):
+        code, out = (5, None) if len(cdata) == 0 or len(cdata) % 160 else oracle_c.call("g1multiexp", cdata)
+        assert errs[i] == code, i
+        assert bytes(outs[i]) == (out if code == 0 else bytes(128)), i
+    calls2 = []
+    for n in (1, 4, 9):
+        d, _ = wl.g2_msm_input(n, 0x7000 + n)
+        calls2.append(d)
+    calls2.append(G2B[:192] + po.fp_to_bytes(7) + ONES)
+    offs2 = [0]
+    for cdata in calls2:
+        offs2.append(offs2[-1] + len(cdata))
+    outs, errs = product.MultiexpBatch(2, b"".join(calls2), offs2)
+    for i, cdata in enumerate(calls2):
+        code, out = oracle_c.call("g2multiexp", cdata)
+        assert errs[i] == code and bytes(outs[i]) == (out if code == 0 else bytes(256)), i

@@ -97,3 +97,13 @@ if "check" in what:
             ev1.record(); torch.cuda.synchronize()
         assert int(d_codes.abs().sum().item()) == 0
         print("G1 batched decode%s over a 2^20-pair MULTIEXP input: %.3f ms -> %.3e points/s" % (" + subgroup check" if sub else "", ev0.elapsed_time(ev1), n / (ev0.elapsed_time(ev1) * 1e-3)), flush=True)
+
+if "batch" in what:
+    for k in (4, 32, 128):
+        ncalls = 16384 if k <= 32 else 4096
+        data = gen_g1(ncalls * k)
+        offs = np.arange(ncalls + 1, dtype=np.uint64) * (160 * k)
+        for rep in range(3):
+            t0 = time.time(); outs, errs = b.MultiexpBatch(1, data, offs); dt = time.time() - t0
+        assert not errs.any() and bytes(outs[0]) == b.G1Multiexp(data[:160 * k])
+        print("G1 MULTIEXP batch: %d calls x %d pairs: %.1f ms -> %.0f calls/s, %.3e pairs/s" % (ncalls, k, dt * 1e3, ncalls / dt, ncalls * k / dt), flush=True)
