@@ -351,3 +351,21 @@ def test_multiexp_batch_matches_single_calls(product, oracle_c):
     for i, cdata in enumerate(calls2):
         code, out = oracle_c.call("g2multiexp", cdata)
         assert errs[i] == code and bytes(outs[i]) == (out if code == 0 else bytes(256)), i
+
+
+def test_random_shapes_against_oracle(product, oracle_c):
+    """Randomised shapes: sizes, repeated points, special scalars, window widths (seeded, bit-exact vs the oracle)."""
+    rnd = random.Random(0xB200)
+    base_pts = [oracle_c.g1_gen_mul(rnd.randrange(po.R)) for _ in range(12)] + [bytes(128), po.encode_g1((0, 2)),
+                po.encode_g1(po.ec_neg(po.FP_OPS, po.G1)), G1B]
+    special = [0, 1, 2, po.R - 1, po.R, po.R + 1, (1 << 256) - 1, 1 << 255, (1 << 128) - 1, 0xFFFF, 1 << 16, (1 << 16) - 1]
+    for trial in range(12):
+        n = rnd.choice([1, 2, 3, 7, 33, 100, 257])
+        data = b"".join(rnd.choice(base_pts) + be32(rnd.choice(special) if rnd.random() < 0.4 else rnd.randrange(1 << 256))
+                        for _ in range(n))
+        want = oracle_c.call("g1multiexp", data)
+        product.set_window(rnd.choice([0, 0, 3, 5, 9, 12, 15, 16]))
+        try:
+            assert product.raw_call("bls12_g1multiexp", data, 128) == want, trial
+        finally:
+            product.set_window(0)

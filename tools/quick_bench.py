@@ -107,3 +107,21 @@ if "batch" in what:
             t0 = time.time(); outs, errs = b.MultiexpBatch(1, data, offs); dt = time.time() - t0
         assert not errs.any() and bytes(outs[0]) == b.G1Multiexp(data[:160 * k])
         print("G1 MULTIEXP batch: %d calls x %d pairs: %.1f ms -> %.0f calls/s, %.3e pairs/s" % (ncalls, k, dt * 1e3, ncalls / dt, ncalls * k / dt), flush=True)
+
+if "single" in what:
+    # latency of ONE call through the legacy ABI (what a drop-in user of bls12_* sees per call)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import workloads as wl
+    for k in (1, 4, 128):
+        d = bytes(gen_g1(k))
+        for rep in range(5):
+            t0 = time.time(); b.G1Multiexp(d); dt = time.time() - t0
+        print("single G1MULTIEXP k=%d: %.2f ms" % (k, dt * 1e3), flush=True)
+    rng = wl.SplitMix64(3)
+    for k in (2, 16):
+        d = wl.pairing_call(k, rng, True)
+        for rep in range(5):
+            t0 = time.time(); out = b.Pairing(d); dt = time.time() - t0
+        assert out[31] == 1
+        print("single PAIRING k=%d: %.2f ms" % (k, dt * 1e3), flush=True)
