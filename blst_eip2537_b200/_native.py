@@ -33,7 +33,7 @@ EXT_FUNCTIONS = [
     "bls12_b200_init", "bls12_b200_shutdown", "bls12_b200_last_error", "bls12_b200_launch_count",
     "bls12_b200_set_window", "bls12_pairing_batch", "bls12_g1multiexp_batch", "bls12_g2multiexp_batch", "bls12_b200_msm_device", "bls12_b200_msm_partial_device", "bls12_b200_msm_partial_host",
     "bls12_b200_msm_combine_device", "bls12_b200_pairing_batch_device", "bls12_b200_g1_generator_mul",
-    "bls12_b200_g2_generator_mul", "bls12_b200_fp_microbench", "bls12_b200_selftest", "bls12_b200_points_check", "bls12_b200_points_check_device", "bls12_b200_set_checked_msm", "bls12_b200_partial_bytes", "bls12_b200_set_profile", "bls12_b200_last_msm_profile", "bls12_b200_last_pairing_profile",
+    "bls12_b200_g2_generator_mul", "bls12_b200_fp_microbench", "bls12_b200_selftest", "bls12_b200_points_check", "bls12_b200_points_check_device", "bls12_b200_set_checked_msm", "bls12_b200_set_pairing_coop_max", "bls12_b200_partial_bytes", "bls12_b200_set_profile", "bls12_b200_last_msm_profile", "bls12_b200_last_pairing_profile",
 ]
 
 
@@ -106,6 +106,8 @@ def lib() -> ctypes.CDLL:
     L.bls12_b200_points_check_device.argtypes = [i32, vp, sz, sz, i32, vp, vp]
     L.bls12_b200_set_checked_msm.restype = None
     L.bls12_b200_set_checked_msm.argtypes = [i32]
+    L.bls12_b200_set_pairing_coop_max.restype = ctypes.c_long
+    L.bls12_b200_set_pairing_coop_max.argtypes = [ctypes.c_long]
     L.bls12_b200_msm_partial_host.restype = i32
     L.bls12_b200_msm_partial_host.argtypes = [i32, vp, sz, u64, vp, vp]
     _LIB = L

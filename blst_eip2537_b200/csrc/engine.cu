@@ -17,6 +17,7 @@
 #include "engine.h"
 #include "msm.cuh"
 #include "pairing.cuh"
+#include "coop12.cuh"
 #include "../../include/eip2537_b200.h"
 
 using namespace b200;
@@ -28,6 +29,11 @@ static std::atomic<uint64_t> g_launches{0};
 static thread_local char g_last_error[256] = "";
 static std::atomic<int> g_forced_window{0};
 static std::atomic<int> g_checked_msm{0};   // opt-in: subgroup-check MULTIEXP inputs (changes error codes vs the reference)
+static long pairing_coop_default() {
+  const char* e = getenv("B200_PAIRING_COOP_MAX");
+  return e ? atol(e) : 256;
+}
+static std::atomic<long> g_pairing_coop_max{pairing_coop_default()};
 
 #define CUDA_TRY(expr)                                                                          \
   do {                                                                                          \
@@ -618,9 +624,19 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
   g_pstage.mark(2, s);
   LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, chunk, ntasks, tasks, call_first, d_errs);
-  LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, ntasks, lines, skip, total_pairs, f);
-  g_pstage.mark(3, s);
-  LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, chunk, call_first, f, d_outs, d_errs);
+  // Two back ends for "multiply the lines into f, final exponentiation, is-one":
+  //   warp-cooperative (coop12.cuh): one warp per call, Fp12 in shared memory -- low latency, all pairs of a
+  //     call share the squarings;
+  //   thread-per-chunk / thread-per-call (pairing.cuh).
+  //   Measured crossover on B200 (profiles/r01_bench.md): the warp path wins below ~300 calls.
+  if ((long)n_calls <= g_pairing_coop_max.load()) {
+    g_pstage.mark(3, s);
+    LAUNCH(k_pairing_call_coop, (unsigned)n_calls, 32, s, n_calls, d_offsets, lines, skip, total_pairs, d_outs, d_errs);
+  } else {
+    LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, ntasks, lines, skip, total_pairs, f);
+    g_pstage.mark(3, s);
+    LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, chunk, call_first, f, d_outs, d_errs);
+  }
   g_pstage.mark(4, s);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
@@ -907,6 +923,9 @@ extern "C" const char* bls12_b200_last_error(void) { return g_last_error; }
 extern "C" uint64_t bls12_b200_launch_count(void) { return g_launches.load(); }
 extern "C" void bls12_b200_set_window(int c) { g_forced_window.store(c); }
 extern "C" void bls12_b200_set_checked_msm(int on) { g_checked_msm.store(on); }
+extern "C" long bls12_b200_set_pairing_coop_max(long n_calls) {
+  return g_pairing_coop_max.exchange(n_calls < 0 ? pairing_coop_default() : n_calls);
+}
 
 // batched point validation: device-resident and host-buffer forms
 extern "C" EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d_points, size_t n, size_t stride_bytes,

@@ -86,6 +86,11 @@ EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d_points, si
  * (src/eip2537.c:340, :401 are TODOs) and the codes would differ. */
 void bls12_b200_set_checked_msm(int on);
 
+/* PAIRING batches of at most n_calls calls run on the warp-cooperative low-latency kernel (one warp per
+ * call), larger ones on the thread-per-chunk throughput kernels.  Default 256 (env B200_PAIRING_COOP_MAX);
+ * n_calls < 0 restores the default.  Returns the previous threshold.  Results are identical either way. */
+long bls12_b200_set_pairing_coop_max(long n_calls);
+
 /* ---- workload generators (synthetic inputs): out[i] = encode(k_i * generator),
  *      k_i = 32-byte big-endian scalars.  Host buffers. */
 EIP2537_ERROR bls12_b200_g1_generator_mul(byte* out, const byte* scalars, size_t n);

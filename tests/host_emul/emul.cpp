@@ -8,6 +8,7 @@
 namespace b200 { unsigned long long g_fp_mul_count = 0; }
 #include "../../blst_eip2537_b200/csrc/msm.cuh"
 #include "../../blst_eip2537_b200/csrc/pairing.cuh"
+#include "../../blst_eip2537_b200/csrc/coop12.cuh"
 
 using namespace b200;
 
@@ -247,6 +248,29 @@ void emul_point_op_fme(unsigned long long* c6, const unsigned char* g1_128, cons
   xyzz_madd(b, q); c6[3] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
   { G2XYZZ t = xyzz_dbl(b); xyzz_add(b, t); } c6[4] = g_fp_mul_count - c0; c0 = g_fp_mul_count;
   b = xyzz_dbl(b); c6[5] = g_fp_mul_count - c0;
+}
+// coop12.cuh operation tables, run sequentially, against the thread-level Fp12 functions.
+// in: 2 x 12 field slots (64 bytes each): f then g.  Returns a bit mask of mismatching operations.
+int emul_coop12_check(const unsigned char* in) {
+  Fp12 f, g;
+  Fp* fe = reinterpret_cast<Fp*>(&f);
+  Fp* ge = reinterpret_cast<Fp*>(&g);
+  for (int i = 0; i < 12; i++) {
+    uint32_t w[16];
+    load_words(w, in + 64 * i, 16); if (fp_from_slot(fe[i], w) < 0) return -1;
+    load_words(w, in + 64 * (12 + i), 16); if (fp_from_slot(ge[i], w) < 0) return -1;
+  }
+  auto same = [](const Fp12& a, const Fp12& b) { return memcmp(&a, &b, sizeof(Fp12)) == 0; };
+  int bad = 0;
+  Fp12 want, got;
+  fp12_sqr(want, f); got = f; coop12_exec_seq<OpSqr>(reinterpret_cast<Fp2*>(&got), nullptr); if (!same(want, got)) bad |= 1;
+  fp12_mul(want, f, g); got = f; coop12_exec_seq<OpMul>(reinterpret_cast<Fp2*>(&got), reinterpret_cast<const Fp2*>(&g)); if (!same(want, got)) bad |= 2;
+  Fp2 line[3] = {g.c0.c0, g.c0.c1, g.c1.c2};
+  want = f; fp12_mul_by_014(want, line[0], line[1], line[2]); got = f; coop12_exec_seq<OpMul014>(reinterpret_cast<Fp2*>(&got), line); if (!same(want, got)) bad |= 4;
+  fp12_cyclotomic_sqr(want, f); got = f; coop12_exec_seq<OpCycSqr>(reinterpret_cast<Fp2*>(&got), nullptr); if (!same(want, got)) bad |= 8;
+  fp12_frob(want, f, 1); got = f; coop12_exec_seq<OpFrob<1>>(reinterpret_cast<Fp2*>(&got), nullptr); if (!same(want, got)) bad |= 16;
+  fp12_frob(want, f, 2); got = f; coop12_exec_seq<OpFrob<2>>(reinterpret_cast<Fp2*>(&got), nullptr); if (!same(want, got)) bad |= 32;
+  return bad;
 }
 int emul_g1_in_subgroup(const unsigned char* in128) {
   uint32_t w[32]; load_words(w, in128, 32);

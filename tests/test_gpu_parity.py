@@ -225,6 +225,37 @@ def test_pairing_batch_matches_oracle(product, oracle_c):
     assert bytes(outs[1]) == bytes(32)
 
 
+def test_pairing_warp_and_thread_kernels_agree(product, oracle_c):
+    """The warp-cooperative (coop12.cuh) and thread-per-chunk pairing kernels give the same bytes and
+    codes as the oracle, on a batch mixing true/false products, k = 1..9 pairs, infinity inputs and a
+    failing call."""
+    data, offs, truth = wl.pairing_batch(24, 0x2537 + 9, kmin=1, kmax=9)
+    inf1, inf2 = bytes(128), bytes(256)
+    order3 = po.encode_g1((0, 2))
+    extra = [inf1 + G2B, G1B + inf2, inf1 + inf2 + G1B + G2B, order3 + G2B,
+             G1B + G2B + po.encode_g1(po.ec_neg(po.FP_OPS, po.G1)) + G2B]
+    calls = [data[offs[j]:offs[j + 1]] for j in range(24)] + extra
+    blob = b"".join(calls)
+    o2 = [0]
+    for cdata in calls:
+        o2.append(o2[-1] + len(cdata))
+    want = [oracle_c.call("pairing", cdata) for cdata in calls]
+    assert [w[0] for w in want[24:]] == [0, 0, 0, 2, 0]
+    assert want[-1][1][31] == 1 and want[26][1][31] == 0
+    results = {}
+    for name, thr in (("warp", 1 << 40), ("thread", 0)):
+        old = product.set_pairing_coop_max(thr)
+        try:
+            outs, errs = product.PairingBatch(blob, o2)
+        finally:
+            product.set_pairing_coop_max(old)
+        results[name] = (list(errs), [bytes(o) for o in outs])
+        for j, (code, out) in enumerate(want):
+            assert errs[j] == code, (name, j, errs[j], code)
+            assert bytes(outs[j]) == (out if code == 0 else bytes(32)), (name, j)
+    assert results["warp"] == results["thread"]
+
+
 def test_g2_subgroup_rejection_in_pairing(product, oracle_c):
     """A point on E'(Fp2) outside G2 must give code 2 (found by hashing x until on-curve)."""
     rnd = random.Random(11)

@@ -124,3 +124,11 @@ def test_pairing_fme_constants(emul, oracle_c):
     c6 = (ctypes.c_ulonglong * 6)()
     emul.emul_point_op_fme(c6, o.encode_g1(o.G1), o.encode_g2(o.G2))
     assert list(c6) == [10, 23, 9, 28, 64, 24]     # madd, dbl+add, dbl over Fp / Fp2
+
+
+def test_coop12_operation_tables(emul):
+    """The warp-cooperative Fp12 operation tables (coop12.cuh), executed sequentially, equal the thread-level functions."""
+    rnd = random.Random(12)
+    for _ in range(20):
+        blob = b"".join(fpb(rnd.randrange(o.P)) for _ in range(24))
+        assert emul.emul_coop12_check(blob) == 0
