@@ -125,6 +125,26 @@ def MultiexpBatch(group: int, data, offsets):
     return outs, errs
 
 
+def MapBatch(group: int, data):
+    """n independent MAP_FP_TO_G1 (group 1, 64-byte elements) / MAP_FP2_TO_G2 (group 2, 128-byte) calls.
+
+    Returns (outs uint8[n, 128 or 256], errs int32[n]); errs[j] is 0 or INVALID_ELEMENT (3).
+    """
+    ptr, nbytes, keep = _buf(data)
+    width = 64 if group == 1 else 128
+    if nbytes % width:
+        raise EIP2537Error(INVALID_LENGTH)
+    n = nbytes // width
+    outs = np.zeros((n, 2 * width), dtype=np.uint8)
+    errs = np.zeros(n, dtype=np.int32)
+    fn = _native.lib().bls12_map_fp_to_g1_batch if group == 1 else _native.lib().bls12_map_fp2_to_g2_batch
+    code = fn(outs.ctypes.data, errs.ctypes.data, ptr, n)
+    del keep
+    if code != SUCCESS:
+        raise EIP2537Error(code)
+    return outs, errs
+
+
 def generator_mul(group: int, scalars) -> bytes:
     """out[i] = encode(k_i * generator) for 32-byte big-endian scalars (synthetic workloads)."""
     ptr, n, keep = _buf(scalars)

@@ -18,6 +18,7 @@
 #include "msm.cuh"
 #include "pairing.cuh"
 #include "coop12.cuh"
+#include "map.cuh"
 #include "../../include/eip2537_b200.h"
 
 using namespace b200;
@@ -543,6 +544,50 @@ static int add_host_impl(const unsigned char* in, unsigned char* out) {
 }
 extern "C" int b200_add_host(int group, const unsigned char* in, unsigned char* out) {
   return group == 1 ? add_host_impl<Fp>(in, out) : add_host_impl<Fp2>(in, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// MAP_FP_TO_G1 / MAP_FP2_TO_G2 (eip2537.c:1093-1163): n independent field elements, one thread each
+// (map.cuh).  outs: n x (128 | 256) bytes, written only for elements whose code is 0; codes[n].
+// ------------------------------------------------------------------------------------------
+template <class F>
+static int map_host_impl(unsigned char* outs, int* codes, const unsigned char* in, size_t n) {
+  if (n == 0) return E_SUCCESS;
+  Engine* ep;
+  int rc = engine_get(&ep, -1);
+  if (rc) return rc;
+  Engine& e = *ep;
+  std::lock_guard<std::mutex> lk(e.mu);
+  const size_t in_bytes = n * (Wire<F>::POINT_WORDS * 2), out_bytes = n * (Wire<F>::POINT_WORDS * 4);
+  if ((rc = e.raw.reserve(in_bytes))) return rc;
+  if ((rc = e.pts.reserve(out_bytes))) return rc;
+  if ((rc = e.pr_errs.reserve(n * sizeof(int)))) return rc;
+  cudaStream_t s = e.stream;
+  CUDA_TRY(cudaMemcpyAsync(e.raw.ptr, in, in_bytes, cudaMemcpyHostToDevice, s));
+  LAUNCH(k_map_to_group<F>, blocks_for(n, 64), 64, s, (const uint32_t*)e.raw.ptr, n, (uint32_t*)e.pts.ptr, (int*)e.pr_errs.ptr);
+  if (n == 1) {          // single call: keep the caller's `out` untouched on error (eip2537.c:1118 encodes last)
+    CUDA_TRY(cudaMemcpyAsync(e.h_out, e.pts.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(e.h_status, e.pr_errs.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    codes[0] = *reinterpret_cast<int*>(e.h_status);
+    if (codes[0] == E_SUCCESS) memcpy(outs, e.h_out, out_bytes);
+    return E_SUCCESS;
+  }
+  CUDA_TRY(cudaMemcpyAsync(outs, e.pts.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(codes, e.pr_errs.ptr, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return E_SUCCESS;
+}
+extern "C" int b200_map_host(int group, const unsigned char* in, unsigned char* out) {
+  int code = E_MEMORY;
+  int rc = group == 1 ? map_host_impl<Fp>(out, &code, in, 1) : map_host_impl<Fp2>(out, &code, in, 1);
+  return rc ? rc : code;
+}
+extern "C" EIP2537_ERROR bls12_map_fp_to_g1_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, size_t n) {
+  return (EIP2537_ERROR)map_host_impl<Fp>(outs, reinterpret_cast<int*>(errs), in, n);
+}
+extern "C" EIP2537_ERROR bls12_map_fp2_to_g2_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, size_t n) {
+  return (EIP2537_ERROR)map_host_impl<Fp2>(outs, reinterpret_cast<int*>(errs), in, n);
 }
 
 // ------------------------------------------------------------------------------------------

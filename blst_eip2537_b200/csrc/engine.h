@@ -9,6 +9,7 @@ extern "C" {
 /* group: 1 = G1 (160-byte pairs, 128-byte result), 2 = G2 (288-byte pairs, 256-byte result) */
 int b200_msm_host(int group, const unsigned char* in, size_t n_pairs, unsigned char* out);
 int b200_add_host(int group, const unsigned char* in, unsigned char* out);
+int b200_map_host(int group, const unsigned char* in, unsigned char* out);
 int b200_pairing_host(const unsigned char* in, size_t k_pairs, unsigned char* out);
 #ifdef __cplusplus
 }

@@ -46,19 +46,15 @@ EIP2537_ERROR bls12_pairing(byte out[32], byte* in, size_t in_len) {
   return (EIP2537_ERROR)b200_pairing_host(in, in_len / 384, out);
 }
 
-/* MAP_FP_TO_G1 / MAP_FP2_TO_G2 are outside the accelerated path:
- * the symbols exist so the Go/Rust bindings link; they report ENCODING_ERROR (a code the
- * reference never produces) after the reference's own length check, so a caller can tell
- * "not provided by this build" from every genuine outcome. */
+/* MAP_FP_TO_G1 / MAP_FP2_TO_G2 (src/eip2537.c:1093-1121, :1135-1163): length check, then the GPU map
+ * (csrc/map.cuh: RFC 9380 SSWU + isogeny + cofactor clearing); an invalid field element gives 3. */
 EIP2537_ERROR bls12_map_fp_to_g1(byte out[128], const byte in[64], size_t in_len) {
-  (void)out; (void)in;
   if (in_len != 64) return EIP2537_INVALID_LENGTH;
-  return EIP2537_ENCODING_ERROR;
+  return (EIP2537_ERROR)b200_map_host(1, in, out);
 }
 EIP2537_ERROR bls12_map_fp2_to_g2(byte out[256], const byte in[128], size_t in_len) {
-  (void)out; (void)in;
   if (in_len != 128) return EIP2537_INVALID_LENGTH;
-  return EIP2537_ENCODING_ERROR;
+  return (EIP2537_ERROR)b200_map_host(2, in, out);
 }
 
 /* ---- gas schedule (src/eip2537.c:1169-1271): EIP-2537 constants, integer arithmetic only */

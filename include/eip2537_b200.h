@@ -47,6 +47,12 @@ EIP2537_ERROR bls12_g1multiexp_batch(byte* outs, EIP2537_ERROR* errs, const byte
 EIP2537_ERROR bls12_g2multiexp_batch(byte* outs, EIP2537_ERROR* errs, const byte* in,
                                      const uint64_t* offsets, size_t n);
 
+/* n independent MAP_FP_TO_G1 / MAP_FP2_TO_G2 calls (src/eip2537.c:1093, :1135) in one submission.
+ * in = n*64 (Fp) / n*128 (Fp2) bytes, outs = n*128 / n*256 bytes, errs[j] = 0 or INVALID_ELEMENT;
+ * for n > 1, outs[j] is unspecified where errs[j] != 0.  Returns non-zero only for a CUDA failure. */
+EIP2537_ERROR bls12_map_fp_to_g1_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, size_t n);
+EIP2537_ERROR bls12_map_fp2_to_g2_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, size_t n);
+
 /* ---- device-resident MSM (group = 1 for G1, 2 for G2).
  *  d_in: n pairs in wire format (160*n / 288*n bytes).  d_out: 128 / 256 encoded bytes.
  *  d_status: one uint64; ~0 on success else (first failing pair index << 8) | code.

@@ -29,7 +29,8 @@ def lib():
     if _LIB is None:
         _LIB = ctypes.CDLL(build())
         for name in ("g1mul", "g1multiexp", "g1multiexp_naive", "g1multiexp_bc",
-                     "g2mul", "g2multiexp", "g2multiexp_naive", "g2multiexp_bc", "pairing"):
+                     "g2mul", "g2multiexp", "g2multiexp_naive", "g2multiexp_bc", "pairing",
+                     "map_fp_to_g1", "map_fp2_to_g2"):
             f = getattr(_LIB, "oracle_bls12_" + name)
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
@@ -54,7 +55,7 @@ _OUTLEN = {"g1": 128, "g2": 256, "pairing": 32}
 
 def call(name: str, data: bytes):
     """-> (err, out bytes or None); `name` like 'g1multiexp', 'g2multiexp_bc', 'pairing'."""
-    outlen = _OUTLEN["pairing" if name == "pairing" else name[:2]]
+    outlen = _OUTLEN["pairing" if name == "pairing" else (name[-2:] if name.startswith("map_") else name[:2])]
     out = ctypes.create_string_buffer(outlen)
     err = getattr(lib(), "oracle_bls12_" + name)(out, bytes(data), len(data))
     return err, (out.raw if err == 0 else None)

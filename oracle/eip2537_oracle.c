@@ -394,6 +394,125 @@ int oracle_bls12_pairing(byte *out, const byte *in, size_t in_len) {
   if (fp12_is_one(&gt)) out[31] = 1;
   return OK;
 }
+/* ------------------------------------------------------------------ MAP_FP_TO_G1 / MAP_FP2_TO_G2
+ * eip2537.c:1093-1121 and :1135-1163: length check, field decode (invalid -> 3), blst_map_to_g1/_g2(p, u, NULL)
+ * [blst-upstream], to_affine, encode.  blst's map is RFC 9380 8.8: simplified SWU onto the isogenous curve
+ * (6.6.2, textbook form with inversions here), isogeny (E.2/E.3, coefficients derived by
+ * oracle/derive_isogeny.py), multiplication by the effective cofactor h_eff.                       */
+static void fp_pow_le(ofp *r, const ofp *a, const unsigned char *e, int nbytes) {
+  ofp acc = OC_ONE, b = *a;
+  for (int i = 8 * nbytes - 1; i >= 0; i--) {
+    fp_sqr(&acc, &acc);
+    if ((e[i >> 3] >> (i & 7)) & 1) fp_mul(&acc, &acc, &b);
+  }
+  *r = acc;
+}
+static void fp2_pow_le(ofp2 *r, const ofp2 *a, const unsigned char *e, int nbytes) {
+  ofp2 acc = OC_ONE2, b = *a;
+  for (int i = 8 * nbytes - 1; i >= 0; i--) {
+    fp2_sqr(&acc, &acc);
+    if ((e[i >> 3] >> (i & 7)) & 1) fp2_mul(&acc, &acc, &b);
+  }
+  *r = acc;
+}
+static int fp_sqrt(ofp *r, const ofp *a) {         /* 1 if a is a square (r = a root) */
+  ofp t, s;
+  fp_pow_le(&t, a, OC_EXP_SQRT_LE, 48);
+  fp_sqr(&s, &t);
+  *r = t;
+  return fp_eq(&s, a);
+}
+static int fp2_sqrt(ofp2 *r, const ofp2 *a) {      /* p = 3 mod 4 "complex method" */
+  if (fp2_is_zero(a)) { *r = *a; return 1; }
+  ofp2 a1, alpha, x0, x, chk, m1 = OC_ONE2;
+  fp2_neg(&m1, &m1);
+  fp2_pow_le(&a1, a, OC_EXP_PM3D4_LE, 48);
+  fp2_sqr(&alpha, &a1); fp2_mul(&alpha, &alpha, a);
+  fp2_mul(&x0, &a1, a);
+  if (fp2_eq(&alpha, &m1)) {                        /* x = i * x0 */
+    fp_neg(&x.c0, &x0.c1); x.c1 = x0.c0;
+  } else {
+    ofp2 b;
+    fp2_add(&b, &alpha, &OC_ONE2);
+    fp2_pow_le(&b, &b, OC_EXP_PM1D2_LE, 48);
+    fp2_mul(&x, &b, &x0);
+  }
+  fp2_sqr(&chk, &x);
+  *r = x;
+  return fp2_eq(&chk, a);
+}
+static int fp_sgn0(const ofp *a) { ofp c; fp_from_mont(&c, a); return (int)(c.l[0] & 1); }
+static int fp2_sgn0(const ofp2 *a) {               /* RFC 9380 4.1 for m = 2 */
+  ofp c0, c1;
+  fp_from_mont(&c0, &a->c0); fp_from_mont(&c1, &a->c1);
+  int s0 = (int)(c0.l[0] & 1), z0 = fp_is_zero(&c0), s1 = (int)(c1.l[0] & 1);
+  return s0 | (z0 & s1);
+}
+
+#define DEFINE_MAP(FE, FF, NXN, NXD, NYN, NYD, ISO, AFF, PT, PF, HEFF, HEFFBITS)                 \
+  static void FF##_curve_rhs(FE *g, const FE *x) {                                                \
+    FE t;                                                                                         \
+    FF##_sqr(&t, x); FF##_add(&t, &t, &ISO##_A); FF##_mul(&t, &t, x); FF##_add(g, &t, &ISO##_B);  \
+  }                                                                                               \
+  static void FF##_horner(FE *r, const FE *cf, int n, const FE *x) {                              \
+    FE acc = cf[n - 1];                                                                           \
+    for (int i = n - 2; i >= 0; i--) { FF##_mul(&acc, &acc, x); FF##_add(&acc, &acc, &cf[i]); }   \
+    *r = acc;                                                                                     \
+  }                                                                                               \
+  static void FF##_map_to_group(AFF *out, const FE *u) {                                          \
+    FE u2, zu2, den, tv1, x1, x, y, g, t;                                                         \
+    FF##_sqr(&u2, u); FF##_mul(&zu2, &ISO##_Z, &u2);                                              \
+    FF##_sqr(&den, &zu2); FF##_add(&den, &den, &zu2);                                             \
+    if (FF##_is_zero(&den)) {                            /* x1 = B / (Z A) */                     \
+      FF##_mul(&t, &ISO##_Z, &ISO##_A); FF##_inv(&t, &t); FF##_mul(&x1, &ISO##_B, &t);            \
+    } else {                                             /* x1 = (-B/A)(1 + 1/den) */             \
+      FE one; memset(&one, 0, sizeof one); memcpy(&one, &OC_ONE, sizeof OC_ONE);                  \
+      FF##_inv(&tv1, &den); FF##_add(&tv1, &tv1, &one);                                           \
+      FF##_inv(&t, &ISO##_A); FF##_mul(&t, &t, &ISO##_B); FF##_neg(&t, &t);                       \
+      FF##_mul(&x1, &t, &tv1);                                                                    \
+    }                                                                                             \
+    FF##_curve_rhs(&g, &x1);                                                                      \
+    if (FF##_sqrt(&y, &g)) x = x1;                                                                \
+    else { FF##_mul(&x, &zu2, &x1); FF##_curve_rhs(&g, &x); FF##_sqrt(&y, &g); }                  \
+    if (FF##_sgn0(u) != FF##_sgn0(&y)) FF##_neg(&y, &y);                                          \
+    /* isogeny E' -> E */                                                                         \
+    FE xn, xd, yn, yd;                                                                            \
+    FF##_horner(&xn, ISO##_XNUM, NXN, &x); FF##_horner(&xd, ISO##_XDEN, NXD, &x);                 \
+    FF##_horner(&yn, ISO##_YNUM, NYN, &x); FF##_horner(&yd, ISO##_YDEN, NYD, &x);                 \
+    AFF e;                                                                                        \
+    memset(&e, 0, sizeof e);                             /* kernel point -> infinity (0,0) */     \
+    if (!FF##_is_zero(&xd) && !FF##_is_zero(&yd)) {                                               \
+      FF##_inv(&xd, &xd); FF##_mul(&e.x, &xn, &xd);                                               \
+      FF##_inv(&yd, &yd); FF##_mul(&e.y, &yn, &yd); FF##_mul(&e.y, &e.y, &y);                     \
+    }                                                                                             \
+    PT p, q;                                                                                      \
+    PF##_from_affine(&p, &e);                                                                     \
+    PF##_mult(&q, &p, HEFF, HEFFBITS);                                                            \
+    PF##_to_affine(out, &q);                                                                      \
+  }
+
+DEFINE_MAP(ofp, fp, 12, 11, 16, 16, OC_ISO1, op1_affine, op1, p1, OC_HEFF1_LE, OC_HEFF1_BITS)
+DEFINE_MAP(ofp2, fp2, 4, 3, 4, 4, OC_ISO2, op2_affine, op2, p2, OC_HEFF2_LE, OC_HEFF2_BITS)
+
+int oracle_bls12_map_fp_to_g1(byte *out, const byte *in, size_t in_len) {
+  if (in_len != 64) return INVALID_LENGTH;
+  ofp u;
+  if (fp_from_bytes(&u, in) < 0) return INVALID_ELEMENT;
+  op1_affine a;
+  fp_map_to_group(&a, &u);
+  encode_g1_point(out, &a);
+  return OK;
+}
+int oracle_bls12_map_fp2_to_g2(byte *out, const byte *in, size_t in_len) {
+  if (in_len != 128) return INVALID_LENGTH;
+  ofp2 u;
+  if (fp2_from_bytes(&u, in) < 0) return INVALID_ELEMENT;
+  op2_affine a;
+  fp2_map_to_group(&a, &u);
+  encode_g2_point(out, &a);
+  return OK;
+}
+
 /* debug/pinning: the GT element as 12 x 48 big-endian bytes, order c0.c0.c0, c0.c0.c1, c0.c1.c0 ... */
 int oracle_pairing_gt(byte *out576, const byte *in, size_t in_len) {
   ofp12 gt;

@@ -527,6 +527,144 @@ def bls12_g2mul(inp):
     return (INVALID_LENGTH, None) if len(inp) != 288 else bls12_g2multiexp(inp)
 
 
+# ----------------------------------------------------------------------------------------
+# MAP_FP_TO_G1 / MAP_FP2_TO_G2 (eip2537.c:1094-1165 -> blst_map_to_g1/_g2 [blst-upstream]):
+# RFC 9380 8.8 -- simplified SWU onto the isogenous curve E' (6.6.2), the 11-/3-isogeny to E (E.2/E.3),
+# cofactor clearing by h_eff (8.8.1/8.8.2).  Isogeny coefficients: oracle/isogeny_constants.json, DERIVED by
+# oracle/derive_isogeny.py (division polynomial + Kohel) and matched bit-for-bit against recalled RFC values.
+# ----------------------------------------------------------------------------------------
+H_EFF_G1 = 0xd201000000010001                                   # 1 - z
+H_EFF_G2 = 0xbc69f08f2ee75b3584c6a0ea91b352888e2a8e9145ad7689986ff031508ffe1329c2f178731db956d82bf015d1212b02ec0ec69d7477c1ae954cbc06689f6a359894c0adebbf6b4e8020005aaa95551
+
+
+def _load_isogeny():
+    import json, os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "isogeny_constants.json")) as fh:
+        doc = json.load(fh)
+    def cv(v):
+        return int(v, 16) if isinstance(v, str) else (int(v[0], 16), int(v[1], 16))
+    out = {}
+    for g in ("g1", "g2"):
+        out[g] = {k: ([cv(e) for e in v] if k in ("x_num", "x_den", "y_num", "y_den") else cv(v))
+                  for k, v in doc[g].items()}
+    return out
+
+
+ISO = _load_isogeny()
+
+
+def fp_sqrt(a):
+    r = pow(a % P, (P + 1) // 4, P)
+    return r if r * r % P == a % P else None
+
+
+def f2_sqrt(a):
+    """A square root of a in Fp2 or None (p = 3 mod 4 'complex method')."""
+    if a == F2_ZERO:
+        return F2_ZERO
+    a1 = f2_pow(a, (P - 3) // 4)
+    alpha = f2_mul(f2_sqr(a1), a)
+    x0 = f2_mul(a1, a)
+    if alpha == (P - 1, 0):
+        x = f2_mul((0, 1), x0)
+    else:
+        b = f2_pow(f2_add(F2_ONE, alpha), (P - 1) // 2)
+        x = f2_mul(b, x0)
+    return x if f2_sqr(x) == a else None
+
+
+def fp_sgn0(a): return a % 2
+def f2_sgn0(a): return (a[0] % 2) | ((1 if a[0] == 0 else 0) & (a[1] % 2))      # RFC 9380 4.1, m = 2
+
+
+def _sswu(o, sqrt, sgn0, A, B, Zc, u):
+    """RFC 9380 6.6.2 simplified SWU for AB != 0 -> affine point on E': y^2 = x^3 + Ax + B."""
+    u2 = o.sqr(u)
+    zu2 = o.mul(Zc, u2)
+    den = o.add(o.sqr(zu2), zu2)
+    if den == o.zero:
+        x1 = o.mul(B, o.inv(o.mul(Zc, A)))
+    else:
+        x1 = o.mul(o.mul(o.neg(B), o.inv(A)), o.add(o.inv(den), o.mul(o.inv(den), den)))   # (-B/A)(1 + tv1)
+    g = lambda x: o.add(o.add(o.mul(o.sqr(x), x), o.mul(A, x)), B)
+    y = sqrt(g(x1))
+    if y is not None:
+        x = x1
+    else:
+        x = o.mul(zu2, x1)
+        y = sqrt(g(x))
+        assert y is not None
+    if sgn0(u) != sgn0(y):
+        y = o.neg(y)
+    return x, y
+
+
+def _horner(o, coeffs, x):
+    r = o.zero
+    for cf in reversed(coeffs):
+        r = o.add(o.mul(r, x), cf)
+    return r
+
+
+def _iso_map(o, iso, pt):
+    x, y = pt
+    xd = _horner(o, iso["x_den"], x)
+    yd = _horner(o, iso["y_den"], x)
+    if xd == o.zero or yd == o.zero:
+        return None                       # kernel of the isogeny -> identity (RFC 9380 E.2 exceptional case)
+    return (o.mul(_horner(o, iso["x_num"], x), o.inv(xd)),
+            o.mul(y, o.mul(_horner(o, iso["y_num"], x), o.inv(yd))))
+
+
+def g2_clear_cofactor_bp(pt):
+    """Budroni-Pintore: [z^2 - z - 1]P + [z - 1]psi(P) + psi^2(2P) (RFC 9380 G.4), z < 0."""
+    o = F2_OPS
+    def mulz(q): return ec_neg(o, ec_mul(o, Z_ABS, q))              # [z]q
+    t1 = mulz(pt)
+    t2 = g2_psi(pt)
+    t3 = g2_psi(g2_psi(ec_add(o, pt, pt)))
+    t3 = ec_add(o, t3, ec_neg(o, t2))
+    t2 = ec_add(o, t1, t2)
+    t2 = mulz(t2)
+    t3 = ec_add(o, t3, t2)
+    t3 = ec_add(o, t3, ec_neg(o, t1))
+    return ec_add(o, t3, ec_neg(o, pt))
+
+
+def map_fp_to_g1(u):
+    iso = ISO["g1"]
+    q = _sswu(FP_OPS, fp_sqrt, fp_sgn0, iso["A"], iso["B"], iso["Z"], u % P)
+    return ec_mul(FP_OPS, H_EFF_G1, _iso_map(FP_OPS, iso, q))
+
+
+def map_fp2_to_g2(u):
+    iso = ISO["g2"]
+    q = _sswu(F2_OPS, f2_sqrt, f2_sgn0, iso["A"], iso["B"], iso["Z"], u)
+    return ec_mul(F2_OPS, H_EFF_G2, _iso_map(F2_OPS, iso, q))
+
+
+def bls12_map_fp_to_g1(inp):
+    """eip2537.c:1093-1121."""
+    inp = bytes(inp)
+    if len(inp) != 64:
+        return INVALID_LENGTH, None
+    st, u = fp_from_bytes(inp)
+    if st < 0:
+        return INVALID_ELEMENT, None
+    return SUCCESS, encode_g1(map_fp_to_g1(u))
+
+
+def bls12_map_fp2_to_g2(inp):
+    """eip2537.c:1135-1163."""
+    inp = bytes(inp)
+    if len(inp) != 128:
+        return INVALID_LENGTH, None
+    st, u = fp2_from_bytes(inp)
+    if st < 0:
+        return INVALID_ELEMENT, None
+    return SUCCESS, encode_g2(map_fp2_to_g2(u))
+
+
 def bls12_pairing(inp, fast_subgroup=False, textbook=False):
     """eip2537.c:1020-1081; per pair: G1 decode, G1 subgroup, G2 decode, G2 subgroup."""
     inp = bytes(inp)

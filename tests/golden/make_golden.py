@@ -41,6 +41,10 @@ def add(fn, name, data, textbook=False):
         code, out = o.bls12_g1multiexp(data)
     elif fn == "g2multiexp":
         code, out = o.bls12_g2multiexp(data)
+    elif fn == "map_fp_to_g1":
+        code, out = o.bls12_map_fp_to_g1(data)
+    elif fn == "map_fp2_to_g2":
+        code, out = o.bls12_map_fp2_to_g2(data)
     else:
         code, out = o.bls12_pairing(data, textbook=textbook)
     row = {"Name": name, "Function": fn, "Input": data.hex()}
@@ -95,5 +99,19 @@ add("pairing", "pairing_fail_g1_off_curve", off1 + G2B)
 add("pairing", "pairing_fail_g2_off_curve", G1B + off2)
 add("pairing", "pairing_fail_order", order3 + off2)
 add("pairing", "pairing_fail_length", G1B + G2B[:200])
+# MAP rows (appended last so the rows above keep their random stream)
+fpb = o.fp_to_bytes
+exc = o.fp_sqrt(-pow(11, -1, P) % P)              # u^2 = -1/Z: the exceptional case of simplified SWU
+for name, u in (("zero", 0), ("one", 1), ("p_minus_1", P - 1), ("sswu_exceptional", exc),
+                ("random_a", rnd.randrange(P)), ("random_b", rnd.randrange(P)), ("random_c", rnd.randrange(P))):
+    add("map_fp_to_g1", "map_fp_to_g1_" + name, fpb(u))
+add("map_fp_to_g1", "map_fp_to_g1_fail_length", fpb(1)[:63])
+add("map_fp_to_g1", "map_fp_to_g1_fail_ge_modulus", bytes(16) + P.to_bytes(48, "big"))
+add("map_fp_to_g1", "map_fp_to_g1_fail_pad", b"\x01" + fpb(1)[1:])
+for name, u in (("zero", (0, 0)), ("one", (1, 0)), ("i", (0, 1)), ("c0_zero_c1_odd", (0, P - 2)),
+                ("random_a", (rnd.randrange(P), rnd.randrange(P))), ("random_b", (rnd.randrange(P), rnd.randrange(P)))):
+    add("map_fp2_to_g2", "map_fp2_to_g2_" + name, fpb(u[0]) + fpb(u[1]))
+add("map_fp2_to_g2", "map_fp2_to_g2_fail_length", fpb(1) + fpb(2) + b"\x00")
+add("map_fp2_to_g2", "map_fp2_to_g2_fail_c1_ge_modulus", fpb(1) + bytes(16) + P.to_bytes(48, "big"))
 json.dump(rows, open(os.path.join(HERE, "eip2537_golden.json"), "w"), indent=1)
 print("wrote", len(rows), "rows")

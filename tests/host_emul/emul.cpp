@@ -9,6 +9,7 @@ namespace b200 { unsigned long long g_fp_mul_count = 0; }
 #include "../../blst_eip2537_b200/csrc/msm.cuh"
 #include "../../blst_eip2537_b200/csrc/pairing.cuh"
 #include "../../blst_eip2537_b200/csrc/coop12.cuh"
+#include "../../blst_eip2537_b200/csrc/map.cuh"
 
 using namespace b200;
 
@@ -295,5 +296,18 @@ int emul_g1_add(unsigned char* out, const unsigned char* in) {
   G1Affine r = xyzz_to_affine(acc);
   uint32_t o[32]; encode_point(o, r); memcpy(out, o, 128);
   return 0;
+}
+// MAP_FP_TO_G1 / MAP_FP2_TO_G2 through the product's map.cuh (straight-line SSWU, isogeny, cofactor clearing)
+int emul_map_fp_to_g1(unsigned char* out128, const unsigned char* in64) {
+  uint32_t wi[16], wo[32]; load_words(wi, in64, 16);
+  int code = map_to_group(wo, wi, (Fp*)nullptr);
+  if (code == 0) memcpy(out128, wo, 128);
+  return code;
+}
+int emul_map_fp2_to_g2(unsigned char* out256, const unsigned char* in128) {
+  uint32_t wi[32], wo[64]; load_words(wi, in128, 32);
+  int code = map_to_group(wo, wi, (Fp2*)nullptr);
+  if (code == 0) memcpy(out256, wo, 256);
+  return code;
 }
 }

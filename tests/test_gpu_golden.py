@@ -9,7 +9,8 @@ import workloads as wl
 pytestmark = pytest.mark.gpu
 
 ABI = {"g1multiexp": ("bls12_g1multiexp", 128), "g2multiexp": ("bls12_g2multiexp", 256), "pairing": ("bls12_pairing", 32),
-       "g1mul": ("bls12_g1mul", 128), "g2mul": ("bls12_g2mul", 256)}
+       "g1mul": ("bls12_g1mul", 128), "g2mul": ("bls12_g2mul", 256),
+       "map_fp_to_g1": ("bls12_map_fp_to_g1", 128), "map_fp2_to_g2": ("bls12_map_fp2_to_g2", 256)}
 
 
 def test_golden_fixtures_on_gpu(product):

@@ -400,3 +400,43 @@ def test_random_shapes_against_oracle(product, oracle_c):
             assert product.raw_call("bls12_g1multiexp", data, 128) == want, trial
         finally:
             product.set_window(0)
+
+
+def test_map_to_curve_single_and_batch(product, oracle_c):
+    """MAP_FP_TO_G1 / MAP_FP2_TO_G2 through the reference ABI and the batch entry point, vs the oracle."""
+    rnd = random.Random(0x2537 + 40)
+    exc = po.fp_sqrt(-pow(11, -1, po.P) % po.P)
+    us = [0, 1, 2, po.P - 1, exc, po.P - exc] + [rnd.randrange(po.P) for _ in range(300)]
+    blob = b"".join(po.fp_to_bytes(u) for u in us)
+    outs, errs = product.MapBatch(1, blob)
+    assert list(errs) == [0] * len(us)
+    for j in range(len(us)):
+        assert oracle_c.call("map_fp_to_g1", blob[64 * j:64 * j + 64]) == (0, bytes(outs[j])), hex(us[j])
+    for j in (0, 4, 17):
+        assert product.MapFpToG1(blob[64 * j:64 * j + 64]) == bytes(outs[j])
+    us2 = [(0, 0), (1, 0), (0, 1), (0, po.P - 2), (po.P - 1, po.P - 1)] + [(rnd.randrange(po.P), rnd.randrange(po.P)) for _ in range(100)]
+    blob2 = b"".join(po.fp_to_bytes(a) + po.fp_to_bytes(b) for a, b in us2)
+    outs2, errs2 = product.MapBatch(2, blob2)
+    assert list(errs2) == [0] * len(us2)
+    for j in range(len(us2)):
+        assert oracle_c.call("map_fp2_to_g2", blob2[128 * j:128 * j + 128]) == (0, bytes(outs2[j])), us2[j]
+    assert product.MapFp2ToG2(blob2[128 * 7:128 * 8]) == bytes(outs2[7])
+    # error codes: length first, then invalid element (pad byte / value >= p); out untouched on error
+    ge_p = bytes(16) + po.P.to_bytes(48, "big")
+    pad = b"\x80" + po.fp_to_bytes(3)[1:]
+    for name, outlen, data, code in (("bls12_map_fp_to_g1", 128, b"", 5), ("bls12_map_fp_to_g1", 128, bytes(63), 5),
+                                     ("bls12_map_fp_to_g1", 128, bytes(128), 5), ("bls12_map_fp_to_g1", 128, ge_p, 3),
+                                     ("bls12_map_fp_to_g1", 128, pad, 3), ("bls12_map_fp2_to_g2", 256, bytes(64), 5),
+                                     ("bls12_map_fp2_to_g2", 256, po.fp_to_bytes(1) + ge_p, 3),
+                                     ("bls12_map_fp2_to_g2", 256, pad + po.fp_to_bytes(1), 3)):
+        got, out = product.raw_call(name, data, outlen)
+        assert got == code and out is None, (name, len(data), got)
+    # a batch keeps per-element codes
+    outs, errs = product.MapBatch(1, po.fp_to_bytes(9) + ge_p + po.fp_to_bytes(10))
+    assert list(errs) == [0, 3, 0]
+    assert bytes(outs[2]) == oracle_c.call("map_fp_to_g1", po.fp_to_bytes(10))[1]
+    # mapped points are valid PAIRING inputs (in G1 / G2): e(P, Q) * e(-P, Q) == 1
+    p1, q2 = bytes(outs[0]), bytes(outs2[5])
+    err, pt = po.decode_g1(p1)
+    neg = po.encode_g1(po.ec_neg(po.FP_OPS, pt))
+    assert product.Pairing(p1 + q2 + neg + q2)[31] == 1

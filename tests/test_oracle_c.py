@@ -87,3 +87,24 @@ def test_arithmetic_progression_generator(oracle_c):
     pts = oracle_c.g2_progression(oracle_c.g2_gen_mul(2), oracle_c.g2_gen_mul(o.R - 1), 4)   # hits infinity at i = 2
     for i in range(4):
         assert pts[256 * i:256 * (i + 1)] == oracle_c.g2_gen_mul((2 - i) % o.R)
+
+
+def test_map_to_curve_c_matches_bigint_model(oracle_c):
+    """MAP_FP_TO_G1 / MAP_FP2_TO_G2: C restatement == Python big-int model; outputs lie in G1 / G2."""
+    rnd = random.Random(0x2537 + 20)
+    exc = o.fp_sqrt(-pow(11, -1, o.P) % o.P)
+    for u in [0, 1, o.P - 1, exc] + [rnd.randrange(o.P) for _ in range(12)]:
+        data = o.fp_to_bytes(u)
+        want = o.bls12_map_fp_to_g1(data)
+        assert oracle_c.call("map_fp_to_g1", data) == want
+        assert oracle_c.lib().oracle_g1_in_subgroup(want[1], 1) == 1
+    for u in [(0, 0), (1, 0), (0, 1)] + [(rnd.randrange(o.P), rnd.randrange(o.P)) for _ in range(4)]:
+        data = o.fp_to_bytes(u[0]) + o.fp_to_bytes(u[1])
+        want = o.bls12_map_fp2_to_g2(data)
+        assert oracle_c.call("map_fp2_to_g2", data) == want
+        assert oracle_c.lib().oracle_g2_in_subgroup(want[1], 1) == 1
+    assert oracle_c.call("map_fp_to_g1", bytes(63)) == (5, None)
+    assert oracle_c.call("map_fp_to_g1", bytes(65)) == (5, None)
+    assert oracle_c.call("map_fp_to_g1", bytes(15) + b"\x01" + bytes(48)) == (3, None)
+    assert oracle_c.call("map_fp2_to_g2", bytes(64)) == (5, None)
+    assert oracle_c.call("map_fp2_to_g2", bytes(64) + bytes(16) + o.P.to_bytes(48, "big")) == (3, None)

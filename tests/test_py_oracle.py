@@ -84,3 +84,82 @@ def test_codec_rules():
     assert o.decode_g1(o.fp_to_bytes(0) + o.fp_to_bytes(3))[0] == o.POINT_NOT_ON_CURVE   # x=0,y!=0 is not infinity
     assert o.bls12_g1multiexp(b"")[0] == o.INVALID_LENGTH and o.bls12_pairing(b"")[0] == o.INVALID_LENGTH
     assert o.bls12_g1multiexp(g + bytes(32)) == (0, bytes(128))
+
+
+# ---- MAP_FP_TO_G1 / MAP_FP2_TO_G2 ------------------------------------------------------------------
+def _on_iso_curve(ops, iso, pt):
+    x, y = pt
+    return ops.sqr(y) == ops.add(ops.add(ops.mul(ops.sqr(x), x), ops.mul(iso["A"], x)), iso["B"])
+
+
+def test_isogeny_constants_are_rederivable_and_copies_agree():
+    """oracle/derive_isogeny.py recomputes both isogenies from the division polynomial (Kohel) and checks the
+    recalled RFC 9380 coefficients; the committed JSON (oracle/ and the product generator's copy in tools/)
+    must equal that derivation."""
+    import json
+    import os
+    import derive_isogeny as d
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    with open(os.path.join(root, "oracle", "isogeny_constants.json")) as fh:
+        a = json.load(fh)
+    with open(os.path.join(root, "tools", "isogeny_constants.json")) as fh:
+        b = json.load(fh)
+    assert a == b
+    g1, g2 = d.g1_isogeny(), d.g2_isogeny()
+    for key in ("x_num", "x_den", "y_num", "y_den"):
+        assert g1[key] == o.ISO["g1"][key]
+        assert [tuple(v) for v in g2[key]] == [tuple(v) for v in o.ISO["g2"][key]]
+    assert (g1["A"], g1["B"], g1["Z"], g1["scale"]) == (o.ISO["g1"]["A"], o.ISO["g1"]["B"], 11, 11)
+    assert g2["scale"] == ((-3) % o.P, 0)
+
+
+def test_isogenous_curve_order_and_isogeny_is_a_homomorphism():
+    rnd = random.Random(0x2537 + 30)
+    iso = o.ISO["g1"]
+    A = iso["A"]
+    def add(p, q):            # group law on E1' (a != 0)
+        if p is None: return q
+        if q is None: return p
+        if p[0] == q[0]:
+            if (p[1] + q[1]) % o.P == 0: return None
+            lam = (3 * p[0] * p[0] + A) * pow(2 * p[1], -1, o.P) % o.P
+        else:
+            lam = (q[1] - p[1]) * pow(q[0] - p[0], -1, o.P) % o.P
+        x = (lam * lam - p[0] - q[0]) % o.P
+        return (x, (lam * (p[0] - x) - p[1]) % o.P)
+    def mul(k, p):
+        r = None
+        while k:
+            if k & 1: r = add(r, p)
+            p = add(p, p); k >>= 1
+        return r
+    pts = []
+    while len(pts) < 2:
+        x = rnd.randrange(o.P)
+        y = o.fp_sqrt((x * x * x + A * x + iso["B"]) % o.P)
+        if y is not None:
+            pts.append((x, y))
+    p, q = pts
+    assert mul(o.H1 * o.R, p) is None                      # #E1'(Fp) = #E1(Fp): E1' is isogenous to E1
+    ip, iq, ipq = (o._iso_map(o.FP_OPS, iso, t) for t in (p, q, add(p, q)))
+    assert o.ec_on_curve(o.FP_OPS, ip) and o.ec_on_curve(o.FP_OPS, iq)
+    assert o.ec_add(o.FP_OPS, ip, iq) == ipq               # iso(P + Q) = iso(P) + iso(Q)
+
+
+def test_map_outputs_in_subgroup_and_g2_cofactor_two_ways():
+    rnd = random.Random(0x2537 + 31)
+    for u in (0, 1, rnd.randrange(o.P)):
+        q = o._sswu(o.FP_OPS, o.fp_sqrt, o.fp_sgn0, o.ISO["g1"]["A"], o.ISO["g1"]["B"], 11, u)
+        assert _on_iso_curve(o.FP_OPS, o.ISO["g1"], q) and o.fp_sgn0(q[1]) == o.fp_sgn0(u)
+        pt = o.map_fp_to_g1(u)
+        assert o.ec_on_curve(o.FP_OPS, pt) and o.g1_in_subgroup(pt)
+    assert o.map_fp_to_g1(5) == o.ec_neg(o.FP_OPS, o.map_fp_to_g1(o.P - 5))     # map(-u) = -map(u)
+    iso = o.ISO["g2"]
+    for u in ((0, 0), (0, 1), (rnd.randrange(o.P), rnd.randrange(o.P))):
+        q = o._sswu(o.F2_OPS, o.f2_sqrt, o.f2_sgn0, iso["A"], iso["B"], iso["Z"], u)
+        assert _on_iso_curve(o.F2_OPS, iso, q) and o.f2_sgn0(q[1]) == o.f2_sgn0(u)
+        e2 = o._iso_map(o.F2_OPS, iso, q)
+        assert o.ec_on_curve(o.F2_OPS, e2)
+        cleared = o.ec_mul(o.F2_OPS, o.H_EFF_G2, e2)
+        assert cleared == o.g2_clear_cofactor_bp(e2)       # recalled h_eff == Budroni-Pintore (RFC 9380 G.4)
+        assert o.g2_in_subgroup(cleared) and cleared == o.map_fp2_to_g2(u)

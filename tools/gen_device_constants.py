@@ -122,6 +122,37 @@ emit("FROB2", [x for v in f2 for x in fp2m(v)])
 emit("G1GEN", [mont(G1[0]), mont(G1[1])])
 emit("G2GEN", fp2m(G2[0]) + fp2m(G2[1]))
 
+# MAP_FP_TO_G1 / MAP_FP2_TO_G2 (RFC 9380 8.8): SSWU curve parameters and isogeny coefficients from
+# tools/isogeny_constants.json (derived and checked by oracle/derive_isogeny.py; a CPU test keeps this copy
+# identical to the oracle's), plus the fixed exponents (raw integers, not Montgomery).
+import json
+import os
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "isogeny_constants.json")) as fh:
+    ISO = json.load(fh)
+
+
+def cv(v):
+    return int(v, 16) if isinstance(v, str) else (int(v[0], 16), int(v[1], 16))
+
+
+i1, i2 = ISO["g1"], ISO["g2"]
+A1, B1c, Z1 = cv(i1["A"]), cv(i1["B"]), cv(i1["Z"])
+emit("ISO1_A", [mont(A1)])
+emit("ISO1_B", [mont(B1c)])
+emit("ISO1_Z", [mont(Z1)])
+sq = pow((-Z1) % P, (P + 1) // 4, P)
+assert sq * sq % P == (-Z1) % P
+emit("ISO1_SQRT_MZ", [mont(sq)])                       # sqrt(-Z) for sqrt_ratio (p = 3 mod 4)
+for key in ("x_num", "x_den", "y_num", "y_den"):
+    emit("ISO1_" + key.upper().replace("_", ""), [mont(cv(v)) for v in i1[key]])
+emit("ISO2_A", fp2m(cv(i2["A"])))
+emit("ISO2_B", fp2m(cv(i2["B"])))
+emit("ISO2_Z", fp2m(cv(i2["Z"])))
+for key in ("x_num", "x_den", "y_num", "y_den"):
+    emit("ISO2_" + key.upper().replace("_", ""), [x for v in i2[key] for x in fp2m(cv(v))])
+emit("EXP_PM3D4", [(P - 3) // 4])
+emit("EXP_PP1D4", [(P + 1) // 4])
+
 print("// GENERATED by tools/gen_device_constants.py -- do not edit.")
 print("// BLS12-381 constants, 12 x 32-bit little-endian limbs, Montgomery form (R = 2^384) unless noted.")
 print("#pragma once")
