@@ -125,3 +125,17 @@ if "single" in what:
             t0 = time.time(); out = b.Pairing(d); dt = time.time() - t0
         assert out[31] == 1
         print("single PAIRING k=%d: %.2f ms" % (k, dt * 1e3), flush=True)
+if "map" in what:
+    # MAP_FP_TO_G1 / MAP_FP2_TO_G2: single-call latency and batch throughput (host buffers, copies included)
+    import numpy as np
+    rng = np.random.default_rng(5)
+    for group, width in ((1, 64), (2, 128)):
+        for n in (1, 1 << 10, 1 << 14, 1 << 17):
+            raw = rng.integers(0, 256, size=(n * (width // 64), 64), dtype=np.uint8)
+            raw[:, :16] = 0
+            raw[:, 16] &= 0x0F                      # < p
+            blob = raw.tobytes()
+            for rep in range(3):
+                t0 = time.time(); outs, errs = b.MapBatch(group, blob); dt = time.time() - t0
+            assert not errs.any()
+            print("MAP group %d n=%d: %.2f ms  (%.0f maps/s)" % (group, n, dt * 1e3, n / dt), flush=True)
