@@ -82,15 +82,23 @@ B200_HD_NI void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
   fp6_add(r.c0, t0, t1);
   r.c1 = c1;
 }
-B200_HD_NI void fp12_sqr(Fp12& r, const Fp12& a) {
-  Fp6 ab, s, t, vab;
-  fp6_mul(ab, a.c0, a.c1);
-  fp6_add(s, a.c0, a.c1);
-  fp6_mul_v(t, a.c1); fp6_add(t, t, a.c0);
-  fp6_mul(s, s, t);
-  fp6_mul_v(vab, ab);
-  fp6_sub(s, s, ab); fp6_sub(r.c0, s, vab);
-  fp6_add(r.c1, ab, ab);
+// complex squaring with two Fp6 temporaries (thread-local memory per thread is what limits the pairing
+// kernels: the resident threads' frames must fit in L2): ab = c0*c1, s = (c0+c1)(c0+v*c1);
+// c0' = s - ab - v*ab, c1' = 2ab
+B200_HD_NI void fp12_sqr_inplace(Fp12& f) {
+  Fp6 ab, s;
+  fp6_mul(ab, f.c0, f.c1);
+  fp6_add(s, f.c0, f.c1);
+  f.c0.c0 = add(f.c0.c0, mul_xi(f.c1.c2)); f.c0.c1 = add(f.c0.c1, f.c1.c0); f.c0.c2 = add(f.c0.c2, f.c1.c1);   // c0 + v*c1
+  fp6_mul(s, s, f.c0);
+  f.c0.c0 = sub(sub(s.c0, ab.c0), mul_xi(ab.c2));
+  f.c0.c1 = sub(sub(s.c1, ab.c1), ab.c0);
+  f.c0.c2 = sub(sub(s.c2, ab.c2), ab.c1);
+  fp6_add(f.c1, ab, ab);
+}
+B200_HD void fp12_sqr(Fp12& r, const Fp12& a) {
+  if (&r != &a) r = a;
+  fp12_sqr_inplace(r);
 }
 B200_HD void fp12_conj(Fp12& r, const Fp12& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
 B200_HD_NI void fp12_inv(Fp12& r, const Fp12& a) {
@@ -102,16 +110,15 @@ B200_HD_NI void fp12_inv(Fp12& r, const Fp12& a) {
 }
 // f *= l0 + l1 w^2 + l4 w^3   (13 Fp2 products)
 B200_HD_NI void fp12_mul_by_014(Fp12& f, const Fp2& l0, const Fp2& l1, const Fp2& l4) {
-  Fp6 aa, bb, s, c1;
-  fp6_mul_by_01(aa, f.c0, l0, l1);
-  fp6_mul_by_1(bb, f.c1, l4);
-  Fp2 o = add(l1, l4);
+  Fp6 s;                                    // one temporary: aa and bb are formed in place in f.c0 / f.c1
   fp6_add(s, f.c0, f.c1);
-  fp6_mul_by_01(c1, s, l0, o);
-  fp6_sub(c1, c1, aa); fp6_sub(c1, c1, bb);
-  fp6_mul_v(bb, bb);
-  fp6_add(f.c0, aa, bb);
-  f.c1 = c1;
+  fp6_mul_by_01(s, s, l0, add(l1, l4));     // (c0 + c1) * (l0, l1 + l4)
+  fp6_mul_by_01(f.c0, f.c0, l0, l1);        // aa
+  fp6_mul_by_1(f.c1, f.c1, l4);             // bb
+  fp6_sub(s, s, f.c0); fp6_sub(s, s, f.c1);
+  fp6_mul_v(f.c1, f.c1);
+  fp6_add(f.c0, f.c0, f.c1);                // aa + v*bb
+  f.c1 = s;
 }
 B200_HD Fp2& fp12_wcoef(Fp12& a, int i) {   // coefficient of w^i
   Fp6& h = (i & 1) ? a.c1 : a.c0;
