@@ -74,11 +74,11 @@ def make_msm_input(group, n, seed, with_expected=True):
     return data, expected
 
 
-def make_pairing_batch(n_calls, seed, first_call=0):
-    """-> (uint8 blob, uint64 offsets[n+1], expected bool[n]); call j has 2 + (j % 15) pairs, every 4th false."""
+def make_pairing_batch(n_calls, seed, first_call=0, fixed_k=0):
+    """-> (uint8 blob, uint64 offsets[n+1], expected bool[n]); call j has 2 + (j % 15) pairs (or fixed_k), every 4th false."""
     import blst_eip2537_b200 as b
     rng = np.random.default_rng(seed)
-    ks = [2 + ((first_call + j) % 15) for j in range(n_calls)]
+    ks = [fixed_k if fixed_k else 2 + ((first_call + j) % 15) for j in range(n_calls)]
     total = sum(ks)
     a = _scalars_below_r(rng, total)
     bb = _scalars_below_r(rng, total)
@@ -224,6 +224,8 @@ def workload_name(args):
         return "G1MULTIEXP single call, 2^%d random points+scalars per GPU (BASELINE configs[1])" % args.logn
     if args.workload == "g2msm":
         return "G2MULTIEXP single call, 2^%d points over Fp2 per GPU (BASELINE configs[2])" % args.logn
+    if args.pairs:
+        return "PAIRING batch: %d independent calls of k=%d pairs, sharded by call (fixed-k sweep of BASELINE configs[3])" % (args.calls, args.pairs)
     return "PAIRING batch: %d independent calls of k=2..16 pairs, sharded by call (BASELINE configs[3])" % args.calls
 
 
@@ -365,7 +367,7 @@ def run_ours(args, rank, world, local_rank):
 
         else:
             calls = args.calls // world
-            blob, offs, truth = make_pairing_batch(calls, 0x2537 + 4 + 1000 * rank, first_call=rank * calls)
+            blob, offs, truth = make_pairing_batch(calls, 0x2537 + 4 + 1000 * rank, first_call=rank * calls, fixed_k=args.pairs)
             total_pairs = int(offs[-1]) // 384
             h_in = torch.from_numpy(blob).pin_memory()
             d_in = h_in.cuda()
@@ -478,7 +480,7 @@ def run_ours(args, rank, world, local_rank):
             # (tests/test_host_emul.py::test_pairing_fme_constants pins them): per pair 2256 (decode + G1/G2
             # subgroup checks) + 1780 (68 line functions) + 2652 (68 sparse Fp12 products); per chunk of <= 3
             # pairs 2232 (62 Fp12 squarings); per call 7688 (final exponentiation) + 54 per extra chunk.
-            ks = [2 + ((rank * calls + j) % 15) for j in range(calls)]
+            ks = [args.pairs if args.pairs else 2 + ((rank * calls + j) % 15) for j in range(calls)]
             nch = [(k + 2) // 3 for k in ks]
             fme = {"decode": DECODE_FME * sum(ks), "lines": 1780 * sum(ks), "accumulate": 2652 * sum(ks) + 2232 * sum(nch),
                    "calls": sum(7688 + 54 * (c - 1) for c in nch)}
@@ -551,6 +553,7 @@ def main():
     ap.add_argument("--workload", default="g1msm", choices=["g1msm", "g2msm", "pairing"])
     ap.add_argument("--logn", type=int, default=None)
     ap.add_argument("--calls", type=int, default=16384)
+    ap.add_argument("--pairs", type=int, default=0, help="pairing workload: fixed pairs per call (default: k = 2..16 mix)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--window", type=int, default=0, help="force the Pippenger window width (developer sweep)")
     args = ap.parse_args()

@@ -81,6 +81,7 @@ struct Buffer {
 
 struct Engine {
   int device = -1;
+  int sm_count = 148;
   bool ready = false;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // H2D copies of streamed MSM chunks (overlap with accumulation)
@@ -109,6 +110,7 @@ static int engine_get(Engine** out, int device) {
       int prev = 0;
       CUDA_TRY(cudaGetDevice(&prev));
       CUDA_TRY(cudaSetDevice(device));
+      CUDA_TRY(cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, device));
       CUDA_TRY(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
       {
         // highest priority: the tail's few blocks must get SM slots as accumulate blocks retire
@@ -646,29 +648,27 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   if ((rc = e.pr_g2.reserve(total_pairs * sizeof(G2Affine)))) return rc;
   if ((rc = e.pr_status.reserve(total_pairs * sizeof(int) + total_pairs + 64))) return rc;
   if ((rc = e.pr_lines.reserve((size_t)ML_STEPS * total_pairs * sizeof(Line)))) return rc;
-  if ((rc = e.pr_tasks.reserve(max_tasks * sizeof(PairingTask) + n_calls * sizeof(uint32_t) + 64))) return rc;
+  if ((rc = e.pr_tasks.reserve(512 + max_tasks * sizeof(PairingTask) + n_calls * sizeof(uint32_t) + 64))) return rc;
   if ((rc = e.pr_f.reserve(max_tasks * sizeof(Fp12)))) return rc;
   G1Affine* g1 = (G1Affine*)e.pr_g1.ptr;
   G2Affine* g2 = (G2Affine*)e.pr_g2.ptr;
   int* pstat = (int*)e.pr_status.ptr;
   unsigned char* skip = (unsigned char*)(pstat + total_pairs);
   Line* lines = (Line*)e.pr_lines.ptr;
-  uint32_t* ntasks = (uint32_t*)e.pr_tasks.ptr;
-  PairingTask* tasks = (PairingTask*)(ntasks + 16);
+  PairingPlanState* plan_state = (PairingPlanState*)e.pr_tasks.ptr;
+  PairingTask* tasks = (PairingTask*)((char*)e.pr_tasks.ptr + 512);
   uint32_t* call_first = (uint32_t*)(tasks + max_tasks);
   Fp12* f = (Fp12*)e.pr_f.ptr;
-  // Pairs per chunk.  3 measured best for the 16384-call batch (2 waves of 168-register threads); larger
-  // chunks share more squarings but lengthen each thread's serial chain (4: 46 ms, 5: 46 ms vs 35 ms), and
-  // limiting residency so the thread-local Fp12 scratch fits the L2 did not pay either (38 ms).
+  // Pairs per chunk: chosen on the device from the batch's own shape (pairing_choose_chunk); B200_PAIRING_CHUNK forces it.
   static const int forced_chunk = getenv("B200_PAIRING_CHUNK") ? atoi(getenv("B200_PAIRING_CHUNK")) : 0;
-  uint32_t chunk = forced_chunk > 0 ? (uint32_t)forced_chunk : (uint32_t)PAIRING_CHUNK;
-  CUDA_TRY(cudaMemsetAsync(ntasks, 0, 64, s));
+  const uint32_t wave = (uint32_t)e.sm_count * 6 * 64;      // resident threads of k_pairing_accumulate: 6 blocks of 64 per SM
+  CUDA_TRY(cudaMemsetAsync(plan_state, 0, sizeof(PairingPlanState), s));
   g_pstage.mark(0, s);
   LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
   g_pstage.mark(1, s);
   LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
   g_pstage.mark(2, s);
-  LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, chunk, ntasks, tasks, call_first, d_errs);
+  LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs);
   // Two back ends for "multiply the lines into f, final exponentiation, is-one":
   //   warp-cooperative (coop12.cuh): one warp per call, Fp12 in shared memory -- low latency, all pairs of a
   //     call share the squarings;
@@ -678,9 +678,11 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
     g_pstage.mark(3, s);
     LAUNCH(k_pairing_call_coop, (unsigned)n_calls, 32, s, n_calls, d_offsets, lines, skip, total_pairs, d_outs, d_errs);
   } else {
-    LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, ntasks, lines, skip, total_pairs, f);
+    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave, (uint32_t)(forced_chunk > 0 ? forced_chunk : 0),
+           plan_state, tasks, call_first);
+    LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, plan_state, lines, skip, total_pairs, f);
     g_pstage.mark(3, s);
-    LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, chunk, call_first, f, d_outs, d_errs);
+    LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
   }
   g_pstage.mark(4, s);
   CUDA_TRY(cudaGetLastError());

@@ -261,7 +261,33 @@ static constexpr int PAIRING_CHUNK = 3;       // default pairs per chunk (the en
 static constexpr int ML_STEPS = 68;          // 63 doubling steps + 5 addition steps (|z| has weight 6)
 
 struct Line { Fp2 l0, l1, l4; };             // l0 + l1*w^2 + l4*w^3, already multiplied by xP / yP
-struct PairingTask { uint32_t first_pair, npairs; };
+struct PairingTask { uint32_t first_pair, npairs, slot; };   // slot: index of the chunk's Miller value in fchunk
+
+// Planning state on the device (one instance per batch, zeroed before k_pairing_count):
+//   tasks_for[c]  number of chunks the batch has when cut into chunks of <= c pairs, c = 1..MAX_CHUNK
+//   len_count[c][l]  how many of those chunks hold exactly l pairs
+//   chunk  the chunk size k_pairing_plan settles on;  ntasks = tasks_for[chunk];  nslots, cursor[l]: allocation cursors
+constexpr int PAIRING_MAX_CHUNK = 6;
+struct PairingPlanState {
+  uint32_t tasks_for[PAIRING_MAX_CHUNK + 1];
+  uint32_t len_count[PAIRING_MAX_CHUNK + 1][PAIRING_MAX_CHUNK + 1];
+  uint32_t cursor[PAIRING_MAX_CHUNK + 1];
+  uint32_t chunk, ntasks, nslots;
+};
+
+// Chunk size rule (measured on B200, profiles/r01_bench.md): k_pairing_accumulate holds `wave` threads at once
+// and is latency-bound below that, so the best cut is the one whose task count just fits one wave -- more
+// tasks start a second wave, fewer leave each thread a longer serial chain.  Smallest c with tasks <= wave
+// (MAX_CHUNK when the batch is many waves long: least total work), then larger chunks while the batch still
+// fills 85 % of a wave (they share more squarings).
+B200_HD uint32_t pairing_choose_chunk(const uint32_t* tasks_for, uint32_t wave, uint32_t forced) {
+  if (forced >= 1 && forced <= (uint32_t)PAIRING_MAX_CHUNK) return forced;
+  uint32_t c = PAIRING_MAX_CHUNK;
+  for (uint32_t t = 1; t <= (uint32_t)PAIRING_MAX_CHUNK; t++)
+    if (tasks_for[t] <= wave) { c = t; break; }
+  while (c < (uint32_t)PAIRING_MAX_CHUNK && (uint64_t)tasks_for[c + 1] * 100 >= (uint64_t)wave * 85) c++;
+  return c;
+}
 
 B200_HD bool in_subgroup(const G1Affine& p) { return g1_in_subgroup(p); }
 B200_HD bool in_subgroup(const G2Affine& p) { return g2_in_subgroup(p); }
@@ -360,12 +386,10 @@ __global__ void __launch_bounds__(64, 6) k_pairing_lines(const G1Affine* __restr
   }
 }
 
-// one thread per call: decide the call's error code (first failing pair, eip2537.c:1033-1053) and cut
-// the call into chunks for k_pairing_accumulate
-__global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* __restrict__ offsets, size_t n_calls,
-                                                      const int* __restrict__ status, uint32_t chunk, uint32_t* ntasks,
-                                                      PairingTask* __restrict__ tasks, uint32_t* __restrict__ call_first_task,
-                                                      int* __restrict__ errs) {
+// one thread per call: decide the call's error code (first failing pair, eip2537.c:1033-1053) and count the
+// chunks it would contribute for every candidate chunk size
+__global__ void __launch_bounds__(128) k_pairing_count(const unsigned long long* __restrict__ offsets, size_t n_calls,
+                                                       const int* __restrict__ status, PairingPlanState* st, int* __restrict__ errs) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_calls) return;
   size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
@@ -373,20 +397,45 @@ __global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* 
   for (size_t j = first; j < last; j++)
     if (status[j] != E_SUCCESS) { errs[i] = status[j]; return; }
   errs[i] = E_SUCCESS;
-  uint32_t k = (uint32_t)(last - first), nch = (k + chunk - 1) / chunk;
-  uint32_t base = atomicAdd(ntasks, nch);
-  call_first_task[i] = base;
-  for (uint32_t c = 0; c < nch; c++) {
-    uint32_t lo = c * chunk, len = k - lo < chunk ? k - lo : chunk;
-    tasks[base + c] = PairingTask{(uint32_t)first + lo, len};
+  uint32_t k = (uint32_t)(last - first);
+  for (uint32_t c = 1; c <= (uint32_t)PAIRING_MAX_CHUNK; c++) {
+    uint32_t full = k / c, rem = k % c;
+    atomicAdd(&st->tasks_for[c], full + (rem ? 1 : 0));
+    if (full) atomicAdd(&st->len_count[c][c], full);
+    if (rem) atomicAdd(&st->len_count[c][rem], 1);
   }
 }
 
-__global__ void __launch_bounds__(64, 6) k_pairing_accumulate(const PairingTask* __restrict__ tasks, const uint32_t* __restrict__ ntasks,
+// one thread per call: cut the call into chunks of the chosen size; tasks are laid out by DECREASING length so
+// that the 32 lanes of a warp walk equally long chains (a warp runs as long as its longest lane)
+__global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* __restrict__ offsets, size_t n_calls,
+                                                      const int* __restrict__ errs, uint32_t wave, uint32_t forced_chunk,
+                                                      PairingPlanState* st, PairingTask* __restrict__ tasks,
+                                                      uint32_t* __restrict__ call_first_task) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_calls) return;
+  const uint32_t chunk = pairing_choose_chunk(st->tasks_for, wave, forced_chunk);
+  if (i == 0) { st->chunk = chunk; st->ntasks = st->tasks_for[chunk]; }
+  if (errs[i] != E_SUCCESS) return;
+  size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
+  uint32_t k = (uint32_t)(last - first), nch = (k + chunk - 1) / chunk;
+  uint32_t slot0 = atomicAdd(&st->nslots, nch);
+  call_first_task[i] = slot0;
+  uint32_t base_of[PAIRING_MAX_CHUNK + 1];
+  uint32_t run = 0;
+  for (int l = PAIRING_MAX_CHUNK; l >= 1; l--) { base_of[l] = run; run += st->len_count[chunk][l]; }
+  for (uint32_t cidx = 0; cidx < nch; cidx++) {
+    uint32_t lo = cidx * chunk, len = k - lo < chunk ? k - lo : chunk;
+    uint32_t pos = base_of[len] + atomicAdd(&st->cursor[len], 1);
+    tasks[pos] = PairingTask{(uint32_t)first + lo, len, slot0 + cidx};
+  }
+}
+
+__global__ void __launch_bounds__(64, 6) k_pairing_accumulate(const PairingTask* __restrict__ tasks, const PairingPlanState* __restrict__ st,
                                                            const Line* __restrict__ lines, const unsigned char* __restrict__ skip,
                                                            size_t total_pairs, Fp12* __restrict__ fchunk) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= *ntasks) return;
+  if (t >= st->ntasks) return;
   PairingTask task = tasks[t];
   Fp12 f;
   fp12_set_one(f);
@@ -406,19 +455,20 @@ __global__ void __launch_bounds__(64, 6) k_pairing_accumulate(const PairingTask*
     }
   }
   fp12_conj(f, f);
-  fchunk[t] = f;
+  fchunk[task.slot] = f;
 }
 
 // one thread per call: product of the chunks' Miller values (blst_fp12_mul, :1061), one final
 // exponentiation (:1070), is-one -> out[31] (:1076)
-__global__ void __launch_bounds__(64) k_pairing_calls(size_t n_calls, const unsigned long long* __restrict__ offsets, uint32_t chunk,
-                                                      const uint32_t* __restrict__ call_first_task, const Fp12* __restrict__ fchunk,
+__global__ void __launch_bounds__(64) k_pairing_calls(size_t n_calls, const unsigned long long* __restrict__ offsets,
+                                                      const PairingPlanState* __restrict__ st, const uint32_t* __restrict__ call_first_task, const Fp12* __restrict__ fchunk,
                                                       uint32_t* __restrict__ outs, const int* __restrict__ errs) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_calls) return;
   uint32_t* out = outs + 8 * i;
   for (int k = 0; k < 8; k++) out[k] = 0;
   if (errs[i] != E_SUCCESS) return;
+  const uint32_t chunk = st->chunk;
   uint32_t npairs = (uint32_t)(offsets[i + 1] / 384 - offsets[i] / 384), nch = (npairs + chunk - 1) / chunk;
   uint32_t base = call_first_task[i];
   Fp12 acc = fchunk[base], cur;

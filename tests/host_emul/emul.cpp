@@ -310,4 +310,8 @@ int emul_map_fp2_to_g2(unsigned char* out256, const unsigned char* in128) {
   if (code == 0) memcpy(out256, wo, 256);
   return code;
 }
+// chunk-size rule of the pairing batch planner (pairing.cuh)
+unsigned emul_pairing_choose_chunk(const unsigned* tasks_for7, unsigned wave, unsigned forced) {
+  return pairing_choose_chunk(tasks_for7, wave, forced);
+}
 }

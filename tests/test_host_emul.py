@@ -162,3 +162,20 @@ def test_map_to_curve_matches_oracle(emul, oracle_c):
     bad = bytes(16) + o.P.to_bytes(48, "big")
     assert emul.emul_map_fp_to_g1(ctypes.create_string_buffer(128), bad) == 3
     assert emul.emul_map_fp2_to_g2(ctypes.create_string_buffer(256), o.fp_to_bytes(1) + bad) == 3
+
+
+def test_pairing_chunk_rule(emul):
+    """pairing_choose_chunk on the batch shapes measured in profiles/r01_bench.md (wave = 148 SMs x 384 threads)."""
+    wave = 148 * 384
+
+    def choose(ks, forced=0):
+        t = (ctypes.c_uint * 7)(0, *[sum((k + c - 1) // c for k in ks) for c in range(1, 7)])
+        return emul.emul_pairing_choose_chunk(t, wave, forced)
+    mix = [2 + (j % 15) for j in range(16384)]
+    assert choose(mix) == 3                       # 54.6 k tasks: just one wave
+    assert choose([2] * 16384) == 1               # 32 k tasks of one pair beat 16 k of two
+    assert choose([16] * 16384) == 6              # many tasks: share more squarings
+    assert choose([5] * 16384) == 2
+    assert choose([9] * 300) == 1                 # small batch: maximum parallelism
+    assert choose([2 + (j % 15) for j in range(131072)]) == 6
+    assert choose(mix, forced=4) == 4
