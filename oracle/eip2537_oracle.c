@@ -14,8 +14,9 @@
  *
  * PARITY UNPINNED: the reference vendors no golden vectors (build.sh:13-52 downloads them).
  * This oracle is pinned instead against oracle/py_oracle.py (big-int model: textbook
- * pairing, naive r*P subgroup tests), public constants and algebraic laws -- see
- * tests/test_oracle_c.py.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * pairing, naive r*P subgroup tests), public constants and algebraic laws, and by published
+ * known answers reproduced exactly (tests/kat.py: RFC 9380 J.9.1/J.9.2/J.10.2 for the map functions,
+ * the geth 2*G1 / 2*G2 vectors, 3*G1) -- see tests/test_oracle_c.py.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load this library.
  */
 #include <stdint.h>

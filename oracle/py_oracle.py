@@ -10,7 +10,8 @@ PARITY PIN STATUS: **parity unpinned by the reference's own vectors** — the re
 downloads all of its golden vectors at build time (/root/reference/build.sh:13-52) and
 vendors none; blst itself is cloned at build time (build.sh:3-11) and is absent.  What pins
 this model instead: the public curve constants, the known answer
-2*G1 (the geth `bls_g1add_(g1+g1=2*g1)` expected value), algebraic laws (r*G=O,
+2*G1 (the geth `bls_g1add_(g1+g1=2*g1)` expected value), 2*G2, 3*G1 and the RFC 9380 hash-to-curve vectors
+J.9.1 / J.9.2 / J.10.2 for MAP_FP_TO_G1 / MAP_FP2_TO_G2 (tests/kat.py, reproduced bit for bit), algebraic laws (r*G=O,
 bilinearity, e(P,Q)e(-P,Q)=1) and agreement between two independent pairing formulations
 in this file (textbook affine Miller loop over E(Fp12) + naive final exponentiation, versus
 the twist/sparse-line/cyclotomic formulation that the C oracle and the CUDA kernels use).

@@ -113,5 +113,26 @@ for name, u in (("zero", (0, 0)), ("one", (1, 0)), ("i", (0, 1)), ("c0_zero_c1_o
     add("map_fp2_to_g2", "map_fp2_to_g2_" + name, fpb(u[0]) + fpb(u[1]))
 add("map_fp2_to_g2", "map_fp2_to_g2_fail_length", fpb(1) + fpb(2) + b"\x00")
 add("map_fp2_to_g2", "map_fp2_to_g2_fail_c1_ge_modulus", fpb(1) + bytes(16) + P.to_bytes(48, "big"))
+# externally published known answers (tests/kat.py): the rows below must reproduce them exactly
+sys.path.insert(0, os.path.join(HERE, ".."))
+import kat  # noqa: E402
+add("map_fp_to_g1", "map_fp_to_g1_rfc9380_J.9.2_msg_empty", fpb(kat.G1_NU_U))
+assert rows[-1]["Expected"] == o.encode_g1(kat.G1_NU_P).hex()
+add("map_fp_to_g1", "map_fp_to_g1_rfc9380_J.9.1_u0", fpb(kat.G1_RO_U0))
+add("map_fp_to_g1", "map_fp_to_g1_rfc9380_J.9.1_u1", fpb(kat.G1_RO_U1))
+# P of J.9.1 = sum of the two single-element maps (clear_cofactor is linear): G1MULTIEXP row with scalars 1, 1
+add("g1multiexp", "g1_multiexp_rfc9380_J.9.1_P_from_two_maps",
+    bytes.fromhex(rows[-2]["Expected"]) + be32(1) + bytes.fromhex(rows[-1]["Expected"]) + be32(1))
+assert rows[-1]["Expected"] == o.encode_g1(kat.G1_RO_P).hex()
+add("map_fp2_to_g2", "map_fp2_to_g2_rfc9380_J.10.2_msg_empty", fpb(kat.G2_NU_U[0]) + fpb(kat.G2_NU_U[1]))
+assert rows[-1]["Expected"] == o.encode_g2(kat.G2_NU_P).hex()
+add("g1multiexp", "g1_mul_generator_by_3_kat", G1B + be32(3))
+assert rows[-1]["Expected"] == o.encode_g1(kat.THREE_G1).hex()
+by_name = {r["Name"]: r for r in rows}
+assert by_name["g1_mul_generator_by_2"]["Expected"] == o.encode_g1(kat.TWO_G1).hex()
+assert by_name["g2_mul_generator_by_2"]["Expected"] == o.encode_g2(kat.TWO_G2).hex()
+for nm in ("g1_mul_generator_by_2", "g2_mul_generator_by_2", "g1_mul_generator_by_3_kat", "map_fp_to_g1_rfc9380_J.9.2_msg_empty",
+           "g1_multiexp_rfc9380_J.9.1_P_from_two_maps", "map_fp2_to_g2_rfc9380_J.10.2_msg_empty"):
+    by_name[nm]["ExternalKAT"] = True
 json.dump(rows, open(os.path.join(HERE, "eip2537_golden.json"), "w"), indent=1)
 print("wrote", len(rows), "rows")

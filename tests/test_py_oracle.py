@@ -163,3 +163,20 @@ def test_map_outputs_in_subgroup_and_g2_cofactor_two_ways():
         cleared = o.ec_mul(o.F2_OPS, o.H_EFF_G2, e2)
         assert cleared == o.g2_clear_cofactor_bp(e2)       # recalled h_eff == Budroni-Pintore (RFC 9380 G.4)
         assert o.g2_in_subgroup(cleared) and cleared == o.map_fp2_to_g2(u)
+
+
+def test_external_known_answers():
+    """tests/kat.py: RFC 9380 J.9.1 / J.9.2 / J.10.2 (msg = "") and the geth 2*G1 / 2*G2 vectors."""
+    import kat
+    iso = o.ISO["g1"]
+    def q_of(u):
+        return o._iso_map(o.FP_OPS, iso, o._sswu(o.FP_OPS, o.fp_sqrt, o.fp_sgn0, iso["A"], iso["B"], iso["Z"], u))
+    assert q_of(kat.G1_NU_U) == kat.G1_NU_Q
+    assert o.map_fp_to_g1(kat.G1_NU_U) == kat.G1_NU_P
+    q0, q1 = q_of(kat.G1_RO_U0), q_of(kat.G1_RO_U1)
+    assert (q0, q1) == (kat.G1_RO_Q0, kat.G1_RO_Q1)
+    assert o.ec_mul(o.FP_OPS, o.H_EFF_G1, o.ec_add(o.FP_OPS, q0, q1)) == kat.G1_RO_P
+    assert o.map_fp2_to_g2(kat.G2_NU_U) == kat.G2_NU_P
+    assert o.ec_add(o.FP_OPS, o.G1, o.G1) == kat.TWO_G1
+    assert o.ec_mul(o.FP_OPS, 3, o.G1) == kat.THREE_G1
+    assert o.ec_add(o.F2_OPS, o.G2, o.G2) == kat.TWO_G2
