@@ -280,6 +280,38 @@ __global__ void __launch_bounds__(32) k_pairing_call_coop(size_t n_calls, const 
     if (one) out[7] = 0x01000000u;
   }
 }
+// One warp per call, for calls with MANY pairs: the Miller values of the call's chunks were accumulated in
+// parallel by k_pairing_accumulate (thread per chunk); the warp multiplies them together, then runs the final
+// exponentiation and the is-one test.  (A lone warp walking hundreds of pairs itself would serialise them.)
+__global__ void __launch_bounds__(32) k_pairing_call_coop_chunks(size_t n_calls, const unsigned long long* __restrict__ offsets,
+                                                                 const PairingPlanState* __restrict__ st,
+                                                                 const uint32_t* __restrict__ call_first_task, const Fp12* __restrict__ fchunk,
+                                                                 uint32_t* __restrict__ outs, const int* __restrict__ errs) {
+  __shared__ Coop12Smem S;
+  const size_t call = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (call >= n_calls) return;
+  uint32_t* out = outs + 8 * call;
+  if (lane < 8) out[lane] = 0;
+  if (errs[call] != E_SUCCESS) return;
+  const uint32_t chunk = st->chunk;
+  const uint32_t npairs = (uint32_t)(offsets[call + 1] / 384 - offsets[call] / 384), nch = (npairs + chunk - 1) / chunk;
+  const uint32_t base = call_first_task[call];
+  if (lane < 6) S.f[lane] = reinterpret_cast<const Fp2*>(&fchunk[base])[lane];
+  __syncwarp();
+#pragma unroll 1
+  for (uint32_t c = 1; c < nch; c++) {
+    if (lane < 6) S.a[lane] = reinterpret_cast<const Fp2*>(&fchunk[base + c])[lane];
+    __syncwarp();
+    coop12_exec<OpMul>(S.f, S.a, S.P);
+  }
+  c12_final_exp(S);
+  if (lane == 0) {
+    bool one = eq(S.f[0], fp2_one());
+    for (int j = 1; j < 6; j++) one = one && is_zero(S.f[j]);
+    if (one) out[7] = 0x01000000u;
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace b200

@@ -674,9 +674,19 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   //     call share the squarings;
   //   thread-per-chunk / thread-per-call (pairing.cuh).
   //   Measured crossover on B200 (profiles/r01_bench.md): the warp path wins below ~300 calls.
-  if ((long)n_calls <= g_pairing_coop_max.load()) {
+  //   A lone warp walks its call's pairs one after the other (~0.55 ms per pair), so small batches of LONG calls
+  //   (more than ~12 pairs per call) accumulate per chunk in parallel first and give the warp only the product of
+  //   the chunk values and the final exponentiation.
+  const bool small_batch = (long)n_calls <= g_pairing_coop_max.load();
+  if (small_batch && total_pairs <= 12 * n_calls) {
     g_pstage.mark(3, s);
     LAUNCH(k_pairing_call_coop, (unsigned)n_calls, 32, s, n_calls, d_offsets, lines, skip, total_pairs, d_outs, d_errs);
+  } else if (small_batch) {
+    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave, (uint32_t)(forced_chunk > 0 ? forced_chunk : 0),
+           plan_state, tasks, call_first);
+    LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, plan_state, lines, skip, total_pairs, f);
+    g_pstage.mark(3, s);
+    LAUNCH(k_pairing_call_coop_chunks, (unsigned)n_calls, 32, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
   } else {
     LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave, (uint32_t)(forced_chunk > 0 ? forced_chunk : 0),
            plan_state, tasks, call_first);

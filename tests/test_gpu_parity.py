@@ -254,6 +254,18 @@ def test_pairing_warp_and_thread_kernels_agree(product, oracle_c):
             assert errs[j] == code, (name, j, errs[j], code)
             assert bytes(outs[j]) == (out if code == 0 else bytes(32)), (name, j)
     assert results["warp"] == results["thread"]
+    # small batch of LONG calls: chunks accumulated in parallel, the warp multiplies the chunk values
+    rng = wl.SplitMix64(0x2537 + 10)
+    long_calls = [wl.pairing_call(30, rng, True), wl.pairing_call(17, rng, False), wl.pairing_call(64, rng, True)]
+    blob = b"".join(long_calls)
+    o3 = [0]
+    for cdata in long_calls:
+        o3.append(o3[-1] + len(cdata))
+    outs, errs = product.PairingBatch(blob, o3)
+    assert list(errs) == [0, 0, 0] and [int(o[31]) for o in outs] == [1, 0, 1]
+    for j, cdata in enumerate(long_calls):
+        assert oracle_c.call("pairing", cdata) == (0, bytes(outs[j]))
+        assert product.Pairing(cdata) == bytes(outs[j])
 
 
 def test_g2_subgroup_rejection_in_pairing(product, oracle_c):
