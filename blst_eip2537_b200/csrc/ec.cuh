@@ -66,7 +66,7 @@ B200_HD_NI XYZZ<F> xyzz_dbl_affine(const Affine<F>& a) {
   F x2 = sqr(a.x);
   F m = add(dbl(x2), x2);
   r.x = sub(sqr(m), dbl(s));
-  r.y = sub(mul(m, sub(s, r.x)), mul(w, a.y));
+  r.y = mul_diff(m, sub(s, r.x), w, a.y);
   r.zz = v;
   r.zzz = w;
   return r;
@@ -84,7 +84,7 @@ B200_HD_NI XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
   F x2 = sqr(p.x);
   F m = add(dbl(x2), x2);
   r.x = sub(sqr(m), dbl(s));
-  r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
+  r.y = mul_diff(m, sub(s, r.x), w, p.y);
   r.zz = mul(v, p.zz);
   r.zzz = mul(w, p.zzz);
   return r;
@@ -108,7 +108,7 @@ B200_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q) {
   F ppp = mul(p, pp);
   F qq = mul(acc.x, pp);
   F x3 = sub(sub(sqr(r), ppp), dbl(qq));
-  acc.y = sub(mul(r, sub(qq, x3)), mul(acc.y, ppp));
+  acc.y = mul_diff(r, sub(qq, x3), acc.y, ppp);
   acc.x = x3;
   acc.zz = mul(acc.zz, pp);
   acc.zzz = mul(acc.zzz, ppp);
@@ -134,7 +134,7 @@ B200_HD_NI void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
   F ppp = mul(p, pp);
   F qq = mul(u1, pp);
   F x3 = sub(sub(sqr(r), ppp), dbl(qq));
-  acc.y = sub(mul(r, sub(qq, x3)), mul(s1, ppp));
+  acc.y = mul_diff(r, sub(qq, x3), s1, ppp);
   acc.x = x3;
   acc.zz = mul(mul(acc.zz, q.zz), pp);
   acc.zzz = mul(mul(acc.zzz, q.zzz), ppp);

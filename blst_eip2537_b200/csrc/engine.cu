@@ -929,6 +929,14 @@ __global__ void __launch_bounds__(128) k_selftest(size_t n, unsigned long long* 
   if ((i & 7) == 1) { b = fp_zero(); }
   if ((i & 7) == 2) { b = a; }
   if (!eq(mul(a, b), mul_portable(a, b))) atomicAdd(&mismatches[0], 1ull);
+  {  // fused a*b - c*d (one reduction) against the two-product form, including the extreme operands p-1 and 1
+    Fp pm1 = fp_load_const(C_P()); pm1.v[0] -= 1;
+    Fp one_raw = fp_zero(); one_raw.v[0] = 1;
+    Fp c2 = (i & 3) == 0 ? one_raw : ((i & 3) == 1 ? pm1 : b);
+    Fp d2 = (i & 4) ? pm1 : a;
+    Fp a2 = (i & 8) ? pm1 : a, b2 = (i & 16) ? pm1 : b;
+    if (!eq(mul_diff(a2, b2, c2, d2), sub(mul_portable(a2, b2), mul_portable(c2, d2)))) atomicAdd(&mismatches[0], 1ull);
+  }
   if (!eq(add(a, b), st_add_ref(a, b, false))) atomicAdd(&mismatches[1], 1ull);
   if (!eq(sub(a, b), st_add_ref(a, b, true))) atomicAdd(&mismatches[2], 1ull);
   Fp q = mul(a, b);

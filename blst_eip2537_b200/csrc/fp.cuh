@@ -325,8 +325,47 @@ B200_D Fp mul(const Fp& a, const Fp& b_in) {
   for (int i = 0; i < 12; i++) r.v[i] = x[i];
   return fp_reduce_once(r, x[12]);
 }
+// a*b - c*d with ONE Montgomery reduction: the rows of both products are accumulated before each reduction
+// row, so the pair costs 2*144 + 156 multiply-accumulates instead of 2*300.  The point formulas end in such a
+// difference (Y3 = R*(Q - X3) - Y1*PPP).  c is negated first, so the accumulator holds a*b + (p-c)*d; it stays
+// below 3p (T' <= (T + (2^32-1)(3p-2)) / 2^32 <= 3p-2 whenever T <= 3p-2), hence two conditional subtractions.
+B200_D Fp mul_diff(const Fp& a, const Fp& b_in, const Fp& c_in, const Fp& d_in) {
+  using namespace detail;
+  const Fp c = sub(fp_zero(), c_in);
+  uint32_t x[13], y[13], b[12], d[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { b[i] = b_in.v[i]; d[i] = d_in.v[i]; x[i] = 0; }
+  x[12] = 0;
+#pragma unroll 1
+  for (int it = 0; it < 6; it++) {
+    uint32_t m;
+    mad_row(x, a.v, b[0]);
+    mul_row(y, a.v + 1, b[0]); y[12] = 0;
+    mad_row(x, c.v, d[0]);
+    mad_row(y, c.v + 1, d[0]);
+    m = x[0] * B200_M0;
+    B200_MADP_ROW(x, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+    B200_MADP_ROW(y, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+    fold(y, x);
+    mad_row(y, a.v, b[1]);
+    mul_row(x, a.v + 1, b[1]); x[12] = 0;
+    mad_row(y, c.v, d[1]);
+    mad_row(x, c.v + 1, d[1]);
+    m = y[0] * B200_M0;
+    B200_MADP_ROW(y, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+    B200_MADP_ROW(x, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+    fold(x, y);
+#pragma unroll
+    for (int i = 0; i < 10; i++) { b[i] = b[i + 2]; d[i] = d[i + 2]; }
+  }
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = x[i];
+  return fp_reduce_once(fp_reduce_once(r, x[12]), 0);
+}
 #else
 B200_HD Fp mul(const Fp& a, const Fp& b);
+B200_HD Fp mul_diff(const Fp& a, const Fp& b, const Fp& c, const Fp& d);
 #endif
 #ifdef B200_COUNT_MULS
 extern unsigned long long g_fp_mul_count;   // tests/host_emul only: counts Fp multiplications per phase
@@ -371,6 +410,7 @@ B200_HD Fp mul_portable(const Fp& a, const Fp& b) {
 }
 #if !(defined(__CUDA_ARCH__) && !defined(B200_FP_PORTABLE))
 B200_HD Fp mul(const Fp& a, const Fp& b) { return mul_portable(a, b); }
+B200_HD Fp mul_diff(const Fp& a, const Fp& b, const Fp& c, const Fp& d) { return sub(mul_portable(a, b), mul_portable(c, d)); }
 #endif
 
 B200_HD Fp sqr(const Fp& a) { return mul(a, a); }
@@ -472,6 +512,7 @@ B200_HD_NI Fp2 sqr(const Fp2& a) {
 B200_HD_NI Fp2 mul_sum2(const Fp2& a1, const Fp2& a2, const Fp2& b1, const Fp2& b2) { return mul(add(a1, a2), add(b1, b2)); }
 B200_HD_NI Fp2 mul_sum1(const Fp2& a1, const Fp2& a2, const Fp2& b) { return mul(add(a1, a2), b); }
 B200_HD_NI Fp2 sqr_sum(const Fp2& a1, const Fp2& a2) { return sqr(add(a1, a2)); }
+B200_HD Fp2 mul_diff(const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d) { return sub(mul(a, b), mul(c, d)); }
 B200_HD_NI Fp2 mul_fp(const Fp2& a, const Fp& k) { Fp2 r; r.c0 = mul(a.c0, k); r.c1 = mul(a.c1, k); return r; }
 B200_HD Fp2 half(const Fp2& a) { Fp2 r; r.c0 = half(a.c0); r.c1 = half(a.c1); return r; }
 B200_HD Fp2 mul_xi(const Fp2& a) { Fp2 r; r.c0 = sub(a.c0, a.c1); r.c1 = add(a.c0, a.c1); return r; }
