@@ -349,7 +349,7 @@ struct Node { XYZZ<F> s, w; };
 
 // level 0: each thread folds `L` consecutive buckets (bucket magnitudes lo+1 .. lo+L) by a running sum
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce_leaf(const XYZZ<F>* __restrict__ buckets, uint32_t nnodes_total, int L,
+__global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fp) ? 4 : 2)) k_reduce_leaf(const XYZZ<F>* __restrict__ buckets, uint32_t nnodes_total, int L,
                                                      Node<F>* __restrict__ nodes) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nnodes_total) return;
