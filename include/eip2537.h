@@ -50,8 +50,9 @@ EIP2537_ERROR bls12_g2multiexp_bc(byte out[256], byte* in, size_t in_len);
 /* src/eip2537.h:54 */
 EIP2537_ERROR bls12_pairing(byte out[32], byte* in, size_t in_len);
 
-/* src/eip2537.h:56-59 -- outside the accelerated hot path; present so
- * the ABI stays complete; see DESIGN.md "Out of scope" for their status */
+/* src/eip2537.h:56-59 (bodies src/eip2537.c:1093-1121, :1135-1163): MAP_FP_TO_G1 / MAP_FP2_TO_G2, GPU-backed
+ * (csrc/map.cuh: RFC 9380 simplified SWU, isogeny, cofactor clearing -- what blst_map_to_g1/_g2 compute).
+ * in_len != 64 / 128 -> INVALID_LENGTH; pad byte or value >= p -> INVALID_ELEMENT; `out` untouched on error. */
 EIP2537_ERROR bls12_map_fp_to_g1(byte out[128], const byte in[64], size_t in_len);
 EIP2537_ERROR bls12_map_fp2_to_g2(byte out[256], const byte in[128], size_t in_len);
 
