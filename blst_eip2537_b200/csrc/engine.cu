@@ -285,7 +285,9 @@ static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s)
   int log_cov = L0_log;                  // log2(buckets covered per node)
   while (nodes_per_win > 1) {
     int remaining_log = plan.log_nb - log_cov;
-    int l_log = remaining_log < 3 ? remaining_log : 3;
+    static const int inner_env = getenv("B200_INNER_LOG") ? atoi(getenv("B200_INNER_LOG")) : 0;
+    const int inner_want = inner_env > 0 ? inner_env : 2;   // children per node = 4; measured: 2 beats 3 by 0.5-1.6 % (G1 2^16..2^20, G2 2^18), 1 and 4 lose
+    int l_log = remaining_log < inner_want ? remaining_log : inner_want;
     size_t out_per_win = nodes_per_win >> l_log;
     LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win * Coop<F>::LANES, 128), 128, s, cur,
            (uint32_t)(plan.nwin * out_per_win), 1 << l_log, log_cov, nxt);
