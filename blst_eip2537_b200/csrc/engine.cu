@@ -273,7 +273,13 @@ static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s)
   const MsmPlan& plan = r.plan;
   int rc;
   static const int leaf_env = getenv("B200_LEAF_LOG") ? atoi(getenv("B200_LEAF_LOG")) : 0;
-  int L0_want = leaf_env > 0 ? leaf_env : (sizeof(F) == sizeof(Fp) ? 3 : 4);   // measured: 8 buckets per leaf for G1, 16 for G2
+  // Buckets per leaf thread (log2), measured per size (profiles/r01_bench.md): small MSMs have few buckets and the
+  // leaf level is pure latency (2 dependent point additions per bucket), so short leaves win; large ones want
+  // fewer, longer leaves (8 buckets for G1, 16 for G2) to keep the cooperative upper levels small.
+  const size_t total_buckets = (size_t)plan.nwin * plan.nb;
+  int L0_auto = total_buckets < (1u << 14) ? 1 : (total_buckets < (1u << 16) ? 2 : 3);
+  if (sizeof(F) != sizeof(Fp) && total_buckets >= (1u << 18)) L0_auto = 4;
+  int L0_want = leaf_env > 0 ? leaf_env : L0_auto;
   int L0_log = plan.log_nb < L0_want ? plan.log_nb : L0_want;
   size_t nodes_per_win = plan.nb >> L0_log;
   if ((rc = e.nodes_a.reserve((size_t)plan.nwin * nodes_per_win * sizeof(Node<F>)))) return rc;
