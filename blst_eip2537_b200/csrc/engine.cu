@@ -139,12 +139,14 @@ static int engine_get(Engine** out, int device) {
 // buckets to fill the GPU and short per-bucket chains -- and flattens at 15-16 where the bucket
 // reduction starts to cost as much as it saves.  Within +-1 of the optimum the time changes by < 5 %.
 static int choose_window(size_t n, bool g2) {
-  (void)g2;
   int forced = g_forced_window.load();
   if (forced >= 2 && forced <= 16) return forced;
   int lg = 0;
   while ((n >> (lg + 1)) != 0) lg++;
   if (lg >= 20) return 16;
+  // measured (tools/sweep_window.py, tools/sweep_window_small.py): ~log2 n, one less in the mid range where the
+  // tail (buckets) still outweighs the accumulation (points); G2's tail is heavier, so it stays one below longer
+  if (lg >= 11 && lg <= (g2 ? 16 : 14)) return lg - 1 > 15 ? 15 : lg - 1;
   return lg < 7 ? 7 : (lg > 15 ? 15 : lg);
 }
 
