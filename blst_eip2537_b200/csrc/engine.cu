@@ -674,7 +674,12 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   const uint32_t wave = (uint32_t)e.sm_count * 6 * 64;      // resident threads of k_pairing_accumulate: 6 blocks of 64 per SM
   CUDA_TRY(cudaMemsetAsync(plan_state, 0, sizeof(PairingPlanState), s));
   g_pstage.mark(0, s);
-  LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
+  const bool small_batch = (long)n_calls <= g_pairing_coop_max.load();
+  if (small_batch) {
+    LAUNCH(k_pairing_decode_split, blocks_for(total_pairs, 32), 64, s, d_raw, total_pairs, g1, g2, pstat);
+  } else {
+    LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
+  }
   g_pstage.mark(1, s);
   LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
   g_pstage.mark(2, s);
@@ -687,7 +692,6 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   //   A lone warp walks its call's pairs one after the other (~0.55 ms per pair), so small batches of LONG calls
   //   (more than ~12 pairs per call) accumulate per chunk in parallel first and give the warp only the product of
   //   the chunk values and the final exponentiation.
-  const bool small_batch = (long)n_calls <= g_pairing_coop_max.load();
   if (small_batch && total_pairs <= 12 * n_calls) {
     g_pstage.mark(3, s);
     LAUNCH(k_pairing_call_coop, (unsigned)n_calls, 32, s, n_calls, d_offsets, lines, skip, total_pairs, d_outs, d_errs);

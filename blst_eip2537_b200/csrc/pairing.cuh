@@ -346,6 +346,45 @@ __global__ void __launch_bounds__(64, 6) k_pairing_decode(const uint32_t* __rest
   if (code == E_SUCCESS) { g1[j] = p; g2[j] = q; }
 }
 
+// Latency variant for small batches: 32 pairs per block of two warps, warp 0 takes the G1 member of each pair, warp 1
+// the G2 member -- the two ladders are independent, so a pair's checks run side by side instead of one after the
+// other (single two-pair call 12.3 -> 11.4 ms).  Large batches keep the kernel above (1-4 % faster there: one warp
+// role per block finishes early).  Code of the pair = G1's if it failed, else G2's: the same precedence.
+__global__ void __launch_bounds__(64, 6) k_pairing_decode_split(const uint32_t* __restrict__ raw, size_t total_pairs,
+                                                       G1Affine* __restrict__ g1, G2Affine* __restrict__ g2, int* __restrict__ status) {
+  __shared__ int code_g1[32];
+  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t j = (size_t)blockIdx.x * 32 + lane;
+  const bool live = j < total_pairs;
+  int code = E_SUCCESS;
+  if (live) {
+    const uint4* src = reinterpret_cast<const uint4*>(raw + j * 96);
+    if (role == 0) {
+      uint32_t w[32];
+      G1Affine p;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { uint4 v = __ldg(src + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+      code = decode_point(p, w);
+      if (code == E_SUCCESS && !g1_in_subgroup(p)) code = E_NOT_IN_SUBGROUP;
+      if (code == E_SUCCESS) g1[j] = p;
+      code_g1[lane] = code;
+    } else {
+      uint32_t w[64];
+      G2Affine q;
+#pragma unroll
+      for (int k = 0; k < 16; k++) { uint4 v = __ldg(src + 8 + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+      code = decode_point(q, w);
+      if (code == E_SUCCESS && !g2_in_subgroup(q)) code = E_NOT_IN_SUBGROUP;
+      if (code == E_SUCCESS) g2[j] = q;
+    }
+  }
+  __syncthreads();
+  if (role == 1 && live) {
+    const int c1 = code_g1[lane];
+    status[j] = c1 != E_SUCCESS ? c1 : code;
+  }
+}
+
 // ---- Miller loop, split in two kernels -------------------------------------------------------
 // The reference runs k independent single-pair Miller loops per call and multiplies them
 // (eip2537.c:1060-1065).  Only the boolean is observable, so here the pairs of a call share the
