@@ -218,6 +218,14 @@ B200_HD_NI Jac<F> jac_scalar_mul(const Affine<F>& p, const uint32_t* k, int nbit
   return acc;
 }
 
+// Jacobian (X, Y, Z) -> XYZZ (X, Y, Z^2, Z^3): the same point, x = X/Z^2, y = Y/Z^3
+template <class F>
+B200_HD XYZZ<F> jac_to_xyzz(const Jac<F>& j) {
+  XYZZ<F> r;
+  r.x = j.x; r.y = j.y; r.zz = sqr(j.z); r.zzz = mul(r.zz, j.z);
+  return r;
+}
+
 using G1Affine = Affine<Fp>;
 using G2Affine = Affine<Fp2>;
 using G1XYZZ = XYZZ<Fp>;

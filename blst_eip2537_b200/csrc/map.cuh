@@ -157,14 +157,6 @@ B200_HD_NI Affine<F> iso_map(const Affine<F>& p) {
   return r;
 }
 
-// Jacobian (X, Y, Z) -> XYZZ (X, Y, Z^2, Z^3): the same point, x = X/Z^2, y = Y/Z^3
-template <class F>
-B200_HD XYZZ<F> jac_to_xyzz(const Jac<F>& j) {
-  XYZZ<F> r;
-  r.x = j.x; r.y = j.y; r.zz = sqr(j.z); r.zzz = mul(r.zz, j.z);
-  return r;
-}
-
 // G1: h_eff = 1 - z = 0xd201000000010001
 B200_HD_NI G1Affine clear_cofactor(const G1Affine& p) {
   if (is_inf(p)) return p;
