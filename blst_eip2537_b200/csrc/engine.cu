@@ -332,14 +332,29 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
   if ((rc = e.partial.reserve(sizeof(XYZZ<Fp2>)))) return rc;
   if ((rc = e.status.reserve(8))) return rc;
   cudaStream_t s = e.stream, cs = e.stream2;
-  const int nchunks = n >= (1u << 18) ? 8 : (n >= (1u << 16) ? 4 : 1);
-  const size_t chunk_n = (n + nchunks - 1) / nchunks;
-  MsmRun<F> r;
-  if ((rc = msm_begin<F>(e, r, n, chunk_n))) return rc;
-  CUDA_TRY(cudaMemsetAsync(e.status.ptr, 0xFF, 8, s));
+  // Chunk boundaries in 32nds of the input.  Geometric sizes: the first copy (which nothing can hide) is small, and
+  // every later copy is shorter than the accumulation of the chunk before it.  B200_STREAM_EVEN=1 restores 8 equal chunks.
+  static const int even_env = getenv("B200_STREAM_EVEN") ? atoi(getenv("B200_STREAM_EVEN")) : 0;
+  static const int cuts_geo[] = {0, 1, 2, 4, 8, 16, 32};
+  static const int cuts_even8[] = {0, 4, 8, 12, 16, 20, 24, 28, 32};
+  static const int cuts_mid[] = {0, 4, 8, 16, 32};
+  static const int cuts_one[] = {0, 32};
+  const int* cuts = cuts_one;
+  int nchunks = 1;
+  if (n >= (1u << 18)) { if (even_env) { cuts = cuts_even8; nchunks = 8; } else { cuts = cuts_geo; nchunks = 6; } }
+  else if (n >= (1u << 16)) { cuts = cuts_mid; nchunks = 4; }
+  size_t chunk_cap = 0;
   for (int c = 0; c < nchunks; c++) {
-    const size_t lo = (size_t)c * chunk_n, hi = lo + chunk_n < n ? lo + chunk_n : n;
-    if (lo >= hi) break;
+    const size_t lo = n * cuts[c] / 32, hi = n * cuts[c + 1] / 32;
+    if (hi - lo > chunk_cap) chunk_cap = hi - lo;
+  }
+  MsmRun<F> r;
+  if ((rc = msm_begin<F>(e, r, n, chunk_cap))) return rc;
+  CUDA_TRY(cudaMemsetAsync(e.status.ptr, 0xFF, 8, s));
+  bool first = true;
+  for (int c = 0; c < nchunks; c++) {
+    const size_t lo = n * cuts[c] / 32, hi = n * cuts[c + 1] / 32;
+    if (lo >= hi) continue;
     unsigned char* dst = (unsigned char*)e.raw.ptr + lo * pair_bytes;
     if (nchunks == 1) {
       CUDA_TRY(cudaMemcpyAsync(dst, in + lo * pair_bytes, (hi - lo) * pair_bytes, cudaMemcpyHostToDevice, s));
@@ -348,7 +363,8 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
       CUDA_TRY(cudaEventRecord(e.ev_group[c], cs));
       CUDA_TRY(cudaStreamWaitEvent(s, e.ev_group[c], 0));
     }
-    if ((rc = msm_feed<F>(e, r, (const uint32_t*)dst, hi - lo, index_base + lo, c == 0, (unsigned long long*)e.status.ptr, s))) return rc;
+    if ((rc = msm_feed<F>(e, r, (const uint32_t*)dst, hi - lo, index_base + lo, first, (unsigned long long*)e.status.ptr, s))) return rc;
+    first = false;
   }
   return msm_tail<F>(e, r, (XYZZ<F>*)e.partial.ptr, s);
 }
