@@ -171,16 +171,29 @@ struct Jac {     // infinity <=> z == 0
 template <class F>
 B200_HD_NI void jac_dbl(Jac<F>& p) {
   if (is_zero(p.z)) return;
-  F a = sqr(p.x), b = sqr(p.y), c = sqr(b);
-  F d = dbl(sub(sub(sqr(add(p.x, b)), a), c));
-  F e = add(dbl(a), a);
-  F f = sqr(e);
-  F z3 = dbl(mul(p.y, p.z));
-  F x3 = sub(f, dbl(d));
-  F c8 = dbl(dbl(dbl(c)));
-  p.y = sub(mul(e, sub(d, x3)), c8);
-  p.x = x3;
-  p.z = z3;
+  if constexpr (sizeof(F) == sizeof(Fp)) {
+    // Fp (a squaring costs a multiplication): D = 4*X*B directly, and Y3 = E*(D - X3) - 8*B*B as ONE fused
+    // difference of products -- 5 multiplications + 1 fused pair instead of 7 multiplications
+    F a = sqr(p.x), b = sqr(p.y);
+    F d = dbl(dbl(mul(p.x, b)));
+    F e = add(dbl(a), a);
+    F z3 = dbl(mul(p.y, p.z));
+    F x3 = sub(sqr(e), dbl(d));
+    p.y = mul_diff(e, sub(d, x3), dbl(dbl(dbl(b))), b);
+    p.x = x3;
+    p.z = z3;
+  } else {
+    F a = sqr(p.x), b = sqr(p.y), c = sqr(b);
+    F d = dbl(sub(sub(sqr(add(p.x, b)), a), c));
+    F e = add(dbl(a), a);
+    F f = sqr(e);
+    F z3 = dbl(mul(p.y, p.z));
+    F x3 = sub(f, dbl(d));
+    F c8 = dbl(dbl(dbl(c)));
+    p.y = sub(mul(e, sub(d, x3)), c8);
+    p.x = x3;
+    p.z = z3;
+  }
 }
 // p += q, q affine and finite; complete (p infinite, p == q, p == -q handled exactly)
 template <class F>
@@ -202,7 +215,7 @@ B200_HD_NI void jac_madd(Jac<F>& p, const Affine<F>& q) {
   F j = mul(h, i);
   F v = mul(p.x, i);
   F x3 = sub(sub(sqr(r), j), dbl(v));
-  F y3 = sub(mul(r, sub(v, x3)), dbl(mul(p.y, j)));
+  F y3 = mul_diff(r, sub(v, x3), dbl(p.y), j);
   F z3 = sub(sub(sqr(add(p.z, h)), z1z1), hh);
   p.x = x3; p.y = y3; p.z = z3;
 }
