@@ -182,7 +182,7 @@ def points_check(group: int, data, stride: int = 0, check_subgroup: bool = True)
 
 
 def set_pairing_coop_max(n_calls: int) -> int:
-    """Batches of <= n_calls PAIRING calls use the warp-per-call kernel (-1: default 256); returns the old value."""
+    """Batches of <= n_calls PAIRING calls use the warp-per-call kernel (-1: default 128); returns the old value."""
     return int(_native.lib().bls12_b200_set_pairing_coop_max(n_calls))
 
 

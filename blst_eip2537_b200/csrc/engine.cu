@@ -32,7 +32,7 @@ static std::atomic<int> g_forced_window{0};
 static std::atomic<int> g_checked_msm{0};   // opt-in: subgroup-check MULTIEXP inputs (changes error codes vs the reference)
 static long pairing_coop_default() {
   const char* e = getenv("B200_PAIRING_COOP_MAX");
-  return e ? atol(e) : 256;
+  return e ? atol(e) : 128;   // measured crossover with the batch planner: ~160 calls (profiles/r01_bench.md)
 }
 static std::atomic<long> g_pairing_coop_max{pairing_coop_default()};
 

@@ -93,7 +93,7 @@ EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d_points, si
 void bls12_b200_set_checked_msm(int on);
 
 /* PAIRING batches of at most n_calls calls run on the warp-cooperative low-latency kernel (one warp per
- * call), larger ones on the thread-per-chunk throughput kernels.  Default 256 (env B200_PAIRING_COOP_MAX);
+ * call), larger ones on the thread-per-chunk throughput kernels.  Default 128 (env B200_PAIRING_COOP_MAX);
  * n_calls < 0 restores the default.  Returns the previous threshold.  Results are identical either way. */
 long bls12_b200_set_pairing_coop_max(long n_calls);
 
