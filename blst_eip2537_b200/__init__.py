@@ -6,5 +6,5 @@ the reference's Go/Rust wrappers; it contains no arithmetic and no CPU fallback.
 """
 from . import _native  # noqa: F401
 from .api import *  # noqa: F401,F403
-from .api import (EIP2537Error, MapBatch, MultiexpBatch, PairingBatch, generator_mul, launch_count, points_check, raw_call,  # noqa: F401
+from .api import (EIP2537Error, MapBatch, MultiexpBatch, PairingBatch, generator_mul, launch_count, points_check, raw_call, raw_call_into,  # noqa: F401
                   set_checked_msm, set_pairing_coop_max, set_window)

@@ -58,6 +58,17 @@ def raw_call(name: str, data, out_len: int):
     return code, (out.raw if code == SUCCESS else None)
 
 
+def raw_call_into(name: str, data, out_len: int, fill: int = 0xA5):
+    """-> (code, out bytes): like raw_call, but `out` is pre-filled with `fill` and returned whatever the
+    code, so tests can check the reference's "`out` is written only on success" rule (eip2537.c:613, :701,
+    :1072-1078 write last)."""
+    ptr, n, keep = _buf(data)
+    out = ctypes.create_string_buffer(bytes([fill]) * out_len, out_len)
+    code = getattr(_native.lib(), name)(out, ptr, n)
+    del keep
+    return code, out.raw
+
+
 def _wrap(name: str, out_len: int):
     def fn(data) -> bytes:
         ptr, n, keep = _buf(data)

@@ -92,19 +92,17 @@ def _on_iso_curve(ops, iso, pt):
     return ops.sqr(y) == ops.add(ops.add(ops.mul(ops.sqr(x), x), ops.mul(iso["A"], x)), iso["B"])
 
 
-def test_isogeny_constants_are_rederivable_and_copies_agree():
+def test_isogeny_constants_are_rederivable():
     """oracle/derive_isogeny.py recomputes both isogenies from the division polynomial (Kohel) and checks the
-    recalled RFC 9380 coefficients; the committed JSON (oracle/ and the product generator's copy in tools/)
-    must equal that derivation."""
+    recalled RFC 9380 coefficients; the committed JSON (the single copy, oracle/isogeny_constants.json, which
+    tools/gen_device_constants.py also reads) must equal that derivation."""
     import json
     import os
     import derive_isogeny as d
     root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
     with open(os.path.join(root, "oracle", "isogeny_constants.json")) as fh:
-        a = json.load(fh)
-    with open(os.path.join(root, "tools", "isogeny_constants.json")) as fh:
-        b = json.load(fh)
-    assert a == b
+        assert json.load(fh) == o.ISO
+    assert not os.path.exists(os.path.join(root, "tools", "isogeny_constants.json"))
     g1, g2 = d.g1_isogeny(), d.g2_isogeny()
     for key in ("x_num", "x_den", "y_num", "y_den"):
         assert g1[key] == o.ISO["g1"][key]

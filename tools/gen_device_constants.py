@@ -123,11 +123,11 @@ emit("G1GEN", [mont(G1[0]), mont(G1[1])])
 emit("G2GEN", fp2m(G2[0]) + fp2m(G2[1]))
 
 # MAP_FP_TO_G1 / MAP_FP2_TO_G2 (RFC 9380 8.8): SSWU curve parameters and isogeny coefficients from
-# tools/isogeny_constants.json (derived and checked by oracle/derive_isogeny.py; a CPU test keeps this copy
-# identical to the oracle's), plus the fixed exponents (raw integers, not Montgomery).
+# oracle/isogeny_constants.json (derived and checked by oracle/derive_isogeny.py; this generator is a developer
+# tool -- the shipped library only sees the constants.cuh it writes), plus the fixed exponents (raw integers).
 import json
 import os
-with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "isogeny_constants.json")) as fh:
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "isogeny_constants.json")) as fh:
     ISO = json.load(fh)
 
 
