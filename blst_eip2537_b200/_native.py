@@ -34,6 +34,8 @@ EXT_FUNCTIONS = [
     "bls12_b200_set_window", "bls12_pairing_batch", "bls12_g1multiexp_batch", "bls12_g2multiexp_batch", "bls12_b200_msm_device", "bls12_b200_msm_partial_device", "bls12_b200_msm_partial_host",
     "bls12_b200_msm_combine_device", "bls12_b200_pairing_batch_device", "bls12_b200_g1_generator_mul",
     "bls12_b200_g2_generator_mul", "bls12_b200_fp_microbench", "bls12_b200_selftest", "bls12_b200_points_check", "bls12_b200_points_check_device", "bls12_b200_set_checked_msm", "bls12_b200_set_pairing_coop_max", "bls12_map_fp_to_g1_batch", "bls12_map_fp2_to_g2_batch", "bls12_b200_partial_bytes", "bls12_b200_set_profile", "bls12_b200_last_msm_profile", "bls12_b200_last_pairing_profile",
+    "bls12_b200_init_multi", "bls12_b200_multi_gpus", "bls12_b200_device_launch_count", "bls12_b200_comm_unique_id", "bls12_b200_comm_init",
+    "bls12_b200_comm_destroy", "bls12_b200_msm_sharded_device", "bls12_b200_msm_sharded_host", "bls12_b200_last_pairing_chunk",
 ]
 
 
@@ -113,5 +115,20 @@ def lib() -> ctypes.CDLL:
     L.bls12_b200_set_pairing_coop_max.argtypes = [ctypes.c_long]
     L.bls12_b200_msm_partial_host.restype = i32
     L.bls12_b200_msm_partial_host.argtypes = [i32, vp, sz, u64, vp, vp]
+    L.bls12_b200_init_multi.restype = i32
+    L.bls12_b200_init_multi.argtypes = [i32]
+    L.bls12_b200_multi_gpus.restype = i32
+    L.bls12_b200_device_launch_count.restype = u64
+    L.bls12_b200_device_launch_count.argtypes = [i32]
+    L.bls12_b200_comm_unique_id.restype = i32
+    L.bls12_b200_comm_unique_id.argtypes = [vp]
+    L.bls12_b200_comm_init.restype = i32
+    L.bls12_b200_comm_init.argtypes = [i32, i32, vp]
+    L.bls12_b200_comm_destroy.restype = None
+    L.bls12_b200_msm_sharded_device.restype = i32
+    L.bls12_b200_msm_sharded_device.argtypes = [i32, vp, sz, u64, vp, vp, vp]
+    L.bls12_b200_msm_sharded_host.restype = i32
+    L.bls12_b200_msm_sharded_host.argtypes = [i32, vp, sz, u64, vp]
+    L.bls12_b200_last_pairing_chunk.restype = i32
     _LIB = L
     return L

@@ -11,13 +11,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
 #include "msm.cuh"
 #include "pairing.cuh"
 #include "coop12.cuh"
+#include "pairing_dot.cuh"
 #include "map.cuh"
 #include "../../include/eip2537_b200.h"
 
@@ -60,76 +65,235 @@ static std::atomic<long> g_pairing_coop_max{pairing_coop_default()};
   do {                                                                                          \
     kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                      \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+    if (tl_pool) tl_pool->launches.fetch_add(1, std::memory_order_relaxed);                     \
+  } while (0)
+
+#define LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                                     \
+  do {                                                                                          \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                 \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+    if (tl_pool) tl_pool->launches.fetch_add(1, std::memory_order_relaxed);                     \
   } while (0)
 
 static inline unsigned blocks_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+struct Engine;
+static thread_local Engine* tl_engine = nullptr;      // the workspace leased by this thread (Buffer::reserve, LAUNCH)
+static void engine_quiesce(Engine* e);
 
 struct Buffer {
   void* ptr = nullptr;
   size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return E_SUCCESS;
-    if (ptr) cudaFree(ptr);
+    if (ptr) {
+      engine_quiesce(tl_engine);          // never free a buffer that an asynchronous submission may still be reading
+      cudaFree(ptr);
+    }
     ptr = nullptr; cap = 0;
     size_t want = bytes + bytes / 8 + 256;
-    CUDA_TRY(cudaMalloc(&ptr, want));
+    cudaError_t err = cudaMalloc(&ptr, want);
+    if (err != cudaSuccess) {
+      (void)cudaGetLastError();           // the failed allocation must not be reported again by a later, valid call
+      ptr = nullptr;
+      snprintf(g_last_error, sizeof g_last_error, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(err));
+      return E_MEMORY;
+    }
     cap = want;
     return E_SUCCESS;
   }
   void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
 };
 
+// Pinned staging ring for PAGEABLE caller memory (Go heap slices, Rust Vec): the caller's bytes are copied into
+// pinned slots by a few host threads while earlier slots are in flight to the device.
+struct StageRing {
+  static constexpr int SLOTS = 4;
+  static constexpr size_t SLOT_BYTES = 8u << 20;
+  unsigned char* slot[SLOTS] = {};
+  cudaEvent_t freed[SLOTS] = {};
+  bool used[SLOTS] = {};
+  int next = 0;
+};
+
+// One WORKSPACE: streams, events, grow-only HBM buffers, pinned result words.  A workspace serves one submission
+// at a time; every device owns a small pool of them (DevicePool), so concurrent host threads run concurrently.
 struct Engine {
   int device = -1;
   int sm_count = 148;
-  bool ready = false;
+  struct DevicePool* pool = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // H2D copies of streamed MSM chunks (overlap with accumulation)
   cudaEvent_t ev_group[8] = {};
   cudaEvent_t ev_tail = nullptr;
-  std::mutex mu;
+  // asynchronous (device-resident) submissions return while their kernels still use the buffers below: `busy` is
+  // recorded on the caller's stream at the end of each of them; the next user of the workspace orders itself after it
+  cudaEvent_t busy = nullptr;
+  bool pending = false;
+  cudaStream_t pending_stream = nullptr;
   // MSM workspaces
   Buffer raw, pts, digits, counts, offsets, block_sums, entries, buckets, nodes_a, nodes_b, partial, out, status, order, tasks, task_partials;
+  Buffer gather;                             // multi-GPU: N records of {partial sum, status key}
   // pairing workspaces
-  Buffer pr_raw, pr_offsets, pr_lines, pr_tasks, pr_g1, pr_g2, pr_status, pr_f, pr_outs, pr_errs;
+  Buffer pr_raw, pr_offsets, pr_lines, pr_tasks, pr_g1, pr_g2, pr_status, pr_f, pr_outs, pr_errs, pr_slots;
   unsigned char* h_out = nullptr;            // pinned: result bytes
   unsigned long long* h_status = nullptr;    // pinned
+  StageRing ring;
+  std::vector<Buffer*> all_buffers() {
+    return {&raw, &pts, &digits, &counts, &offsets, &block_sums, &entries, &buckets, &nodes_a, &nodes_b, &partial, &out, &status,
+            &order, &tasks, &task_partials, &gather, &pr_raw, &pr_offsets, &pr_lines, &pr_tasks, &pr_g1, &pr_g2, &pr_status, &pr_f,
+            &pr_outs, &pr_errs, &pr_slots};
+  }
 };
 
-static constexpr int MAX_DEVICES = 16;
-static Engine g_engines[MAX_DEVICES];
-static std::mutex g_init_mu;
+static void engine_quiesce(Engine* e) {
+  if (e && e->pending) { cudaEventSynchronize(e->busy); e->pending = false; }
+}
 
-static int engine_get(Engine** out, int device) {
-  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
-  if (device >= MAX_DEVICES) { snprintf(g_last_error, sizeof g_last_error, "device %d out of range", device); return E_MEMORY; }
-  Engine& e = g_engines[device];
-  if (!e.ready) {
-    std::lock_guard<std::mutex> lk(g_init_mu);
-    if (!e.ready) {
-      int prev = 0;
-      CUDA_TRY(cudaGetDevice(&prev));
-      CUDA_TRY(cudaSetDevice(device));
-      CUDA_TRY(cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, device));
-      CUDA_TRY(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
-      {
-        // highest priority: the tail's few blocks must get SM slots as accumulate blocks retire
-        int lo = 0, hi = 0;
-        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&e.stream2, cudaStreamNonBlocking, hi));
-      }
-      for (int k = 0; k < 8; k++) CUDA_TRY(cudaEventCreateWithFlags(&e.ev_group[k], cudaEventDisableTiming));
-      CUDA_TRY(cudaEventCreateWithFlags(&e.ev_tail, cudaEventDisableTiming));
-      CUDA_TRY(cudaMallocHost((void**)&e.h_out, 4096));
-      CUDA_TRY(cudaMallocHost((void**)&e.h_status, 64));
-      CUDA_TRY(cudaSetDevice(prev));
-      e.device = device;
-      e.ready = true;
-    }
+static constexpr int MAX_DEVICES = 16;
+struct DevicePool {
+  int device = -1;
+  int sm_count = 148;
+  std::atomic<bool> ready{false};
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<Engine*> idle;
+  int created = 0;
+  std::atomic<uint64_t> launches{0};
+};
+static DevicePool g_pools[MAX_DEVICES];
+static std::mutex g_init_mu;
+static thread_local DevicePool* tl_pool = nullptr;
+static int max_workspaces() {
+  static const int v = getenv("B200_WORKSPACES") ? atoi(getenv("B200_WORKSPACES")) : 4;
+  return v < 1 ? 1 : (v > 16 ? 16 : v);
+}
+
+static void engine_destroy(Engine* e) {
+  if (!e) return;
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (Buffer* b : e->all_buffers()) b->release();
+  if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->h_status) cudaFreeHost(e->h_status);
+  for (int k = 0; k < StageRing::SLOTS; k++) {
+    if (e->ring.slot[k]) cudaFreeHost(e->ring.slot[k]);
+    if (e->ring.freed[k]) cudaEventDestroy(e->ring.freed[k]);
   }
-  *out = &e;
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
+  for (int k = 0; k < 8; k++) if (e->ev_group[k]) cudaEventDestroy(e->ev_group[k]);
+  if (e->ev_tail) cudaEventDestroy(e->ev_tail);
+  if (e->busy) cudaEventDestroy(e->busy);
+  delete e;
+}
+
+// create one workspace on the CURRENT device (== pool.device); partially created resources are destroyed on failure
+static int engine_create(DevicePool& pool, Engine** out) {
+  Engine* e = new Engine();
+  e->device = pool.device; e->sm_count = pool.sm_count; e->pool = &pool;
+  cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) {
+    int lo = 0, hi = 0;
+    err = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi);
+  }
+  for (int k = 0; k < 8 && err == cudaSuccess; k++) err = cudaEventCreateWithFlags(&e->ev_group[k], cudaEventDisableTiming);
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_tail, cudaEventDisableTiming);
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->busy, cudaEventDisableTiming);
+  if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_out, 4096);
+  if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_status, 64);
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    snprintf(g_last_error, sizeof g_last_error, "workspace creation on device %d: %s", pool.device, cudaGetErrorString(err));
+    engine_destroy(e);
+    return E_MEMORY;
+  }
+  *out = e;
   return E_SUCCESS;
 }
+
+static int pool_get(DevicePool** out, int device) {
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= MAX_DEVICES) { snprintf(g_last_error, sizeof g_last_error, "device %d out of range", device); return E_MEMORY; }
+  DevicePool& p = g_pools[device];
+  if (!p.ready.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (!p.ready.load(std::memory_order_relaxed)) {
+      int count = 0;
+      CUDA_TRY(cudaGetDeviceCount(&count));
+      if (device >= count) { snprintf(g_last_error, sizeof g_last_error, "device %d of %d does not exist", device, count); return E_MEMORY; }
+      CUDA_TRY(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, device));
+      p.device = device;
+      p.ready.store(true, std::memory_order_release);
+    }
+  }
+  *out = &p;
+  return E_SUCCESS;
+}
+
+// RAII lease of one workspace of a device.  Host-buffer entry points run on the workspace's own stream and finish
+// with a stream synchronize; device-resident entry points enqueue on the CALLER's stream and call submitted().
+struct Lease {
+  Engine* e = nullptr;
+  DevicePool* pool = nullptr;
+  int prev_device = -1;
+  Engine* prev_tl_engine = nullptr;
+  DevicePool* prev_tl_pool = nullptr;
+  // `async_stream`: the stream an asynchronous submission will use (its identity lets back-to-back submissions on
+  // one stream reuse a workspace without any wait: stream order already serialises them)
+  int acquire(int device, bool is_async = false, cudaStream_t async_stream = nullptr) {
+    (void)cudaGetLastError();        // a stale, non-sticky error of an earlier call must not fail this one
+    int rc = pool_get(&pool, device);
+    if (rc) return rc;
+    CUDA_TRY(cudaGetDevice(&prev_device));
+    if (prev_device != pool->device) CUDA_TRY(cudaSetDevice(pool->device));
+    {
+      std::unique_lock<std::mutex> lk(pool->mu);
+      for (;;) {
+        if (!pool->idle.empty()) {
+          size_t pick = pool->idle.size() - 1;
+          for (size_t i = 0; i < pool->idle.size(); i++) {       // prefer a workspace that needs no wait
+            Engine* c = pool->idle[i];
+            if (!c->pending || (is_async && c->pending_stream == async_stream)) { pick = i; break; }
+          }
+          e = pool->idle[pick];
+          pool->idle.erase(pool->idle.begin() + pick);
+          break;
+        }
+        if (pool->created < max_workspaces()) {
+          pool->created++;
+          lk.unlock();
+          rc = engine_create(*pool, &e);
+          if (rc) { lk.lock(); pool->created--; lk.unlock(); pool->cv.notify_one(); restore(); return rc; }
+          break;
+        }
+        pool->cv.wait(lk);
+      }
+    }
+    if (e->pending && !(is_async && e->pending_stream == async_stream)) engine_quiesce(e);
+    prev_tl_engine = tl_engine; prev_tl_pool = tl_pool;
+    tl_engine = e; tl_pool = pool;
+    return E_SUCCESS;
+  }
+  // asynchronous submission finished enqueuing on `s`
+  void submitted(cudaStream_t s) {
+    if (!e) return;
+    if (cudaEventRecord(e->busy, s) == cudaSuccess) { e->pending = true; e->pending_stream = s; }
+    else { (void)cudaGetLastError(); cudaStreamSynchronize(s); e->pending = false; }
+  }
+  void restore() {
+    if (prev_device >= 0 && pool && prev_device != pool->device) cudaSetDevice(prev_device);
+    prev_device = -1;
+  }
+  ~Lease() {
+    if (e) {
+      tl_engine = prev_tl_engine; tl_pool = prev_tl_pool;
+      { std::lock_guard<std::mutex> lk(pool->mu); pool->idle.push_back(e); }
+      pool->cv.notify_one();
+    }
+    restore();
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // MSM
@@ -152,15 +316,22 @@ static int choose_window(size_t n, bool g2) {
 
 // optional per-stage timing (bench.py's roofline leg): events around the stages of the last MSM
 static std::atomic<int> g_profile{0};
+// (developer / bench mode: bls12_b200_set_profile(1) is meant for ONE caller thread on one device at a time)
 struct StageTimer {
   static constexpr int N = 8;
   cudaEvent_t ev[N] = {};
   bool made = false;
   int used = 0;
+  std::mutex mu;
   void mark(int i, cudaStream_t s) {
     if (!g_profile.load()) return;
-    if (!made) { for (int k = 0; k < N; k++) cudaEventCreate(&ev[k]); made = true; }
-    cudaEventRecord(ev[i], s);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!made) {
+      for (int k = 0; k < N; k++)
+        if (cudaEventCreate(&ev[k]) != cudaSuccess) { (void)cudaGetLastError(); return; }
+      made = true;
+    }
+    if (cudaEventRecord(ev[i], s) != cudaSuccess) { (void)cudaGetLastError(); return; }
     if (i + 1 > used) used = i + 1;
   }
 };
@@ -189,6 +360,11 @@ static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
   r.chunk_cap = chunk_n;
   const size_t nbt = r.nbt;
   int rc;
+  // offsets, cursors and sorted entries are 32-bit and a point index carries its sign in bit 31
+  if (chunk_n >= ((size_t)1 << 31) || chunk_n * (size_t)plan.nwin > 0xFFFFFFFFull) {
+    snprintf(g_last_error, sizeof g_last_error, "MULTIEXP of %zu pairs per chunk exceeds the 32-bit sort index: shard it (bls12_b200_init_multi) or split the call", chunk_n);
+    return E_MEMORY;
+  }
   if ((rc = e.pts.reserve(chunk_n * sizeof(Affine<F>)))) return rc;
   if ((rc = e.digits.reserve(chunk_n * plan.nwin * sizeof(int)))) return rc;
   if ((rc = e.counts.reserve(2 * nbt * sizeof(uint32_t)))) return rc;       // counts + cursors
@@ -271,7 +447,8 @@ static int msm_feed(Engine& e, MsmRun<F>& r, const uint32_t* d_raw, size_t n, ui
 // other windows on a second stream was tried and measured slower: 11.7 vs 10.7 ms for 2^20 G1 -- the
 // dependent chains need the multiply pipe to themselves.)
 template <class F>
-static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s) {
+static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, const unsigned long long* d_status, unsigned long long* d_status_copy,
+                    cudaStream_t s) {
   const MsmPlan& plan = r.plan;
   int rc;
   static const int leaf_env = getenv("B200_LEAF_LOG") ? atoi(getenv("B200_LEAF_LOG")) : 0;
@@ -304,7 +481,7 @@ static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s)
     log_cov += l_log;
   }
   g_stage.mark(3, s);
-  LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan, d_partial);
+  LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan, d_partial, d_status, d_status_copy);
   g_stage.mark(4, s);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
@@ -313,25 +490,119 @@ static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, cudaStream_t s)
 // device-resident input: one chunk
 template <class F>
 static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t index_base, XYZZ<F>* d_partial,
-                        unsigned long long* d_status, cudaStream_t s) {
+                        unsigned long long* d_status, unsigned long long* d_status_copy, cudaStream_t s) {
   MsmRun<F> r;
   int rc;
   if ((rc = msm_begin<F>(e, r, n, n))) return rc;
   if ((rc = msm_feed<F>(e, r, d_raw, n, index_base, true, d_status, s))) return rc;
-  return msm_tail<F>(e, r, d_partial, s);
+  return msm_tail<F>(e, r, d_partial, d_status, d_status_copy, s);
+}
+
+// ---- pageable caller memory ------------------------------------------------------------------
+// Go passes heap slices (go/blst_eip2537.go:74), Rust passes Vec / stack arrays: ordinary pageable memory, which
+// cudaMemcpyAsync moves at ~7 GB/s through the driver's own bounce buffer.  Here a small pool of host threads
+// copies the caller's bytes into the workspace's pinned ring while earlier ring slots are in flight over PCIe.
+struct CopyPool {
+  struct Job { unsigned char* d; const unsigned char* s; size_t n; std::atomic<int>* left; };
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<Job> q;
+  bool stop = false;
+  int nthreads = 0;
+  void start() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (nthreads) return;
+    int want = getenv("B200_COPY_THREADS") ? atoi(getenv("B200_COPY_THREADS")) : 4;
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && want > hw / 2) want = hw / 2;
+    if (want < 1) want = 1;
+    nthreads = want;
+    for (int i = 0; i < want; i++) th.emplace_back([this] { this->run(); });
+  }
+  void run() {
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this] { return stop || !q.empty(); });
+        if (stop && q.empty()) return;
+        j = q.back();
+        q.pop_back();
+      }
+      memcpy(j.d, j.s, j.n);
+      j.left->fetch_sub(1, std::memory_order_release);
+    }
+  }
+  // dst <- src with every pool thread and the caller taking a share
+  void copy(unsigned char* d, const unsigned char* s, size_t n) {
+    start();
+    const int parts = nthreads + 1;
+    const size_t per = ((n / parts) + 4095) & ~(size_t)4095;
+    std::atomic<int> left{0};
+    size_t off = 0;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (int i = 0; i < nthreads && off + per < n; i++, off += per) { left.fetch_add(1); q.push_back(Job{d + off, s + off, per, &left}); }
+    }
+    cv.notify_all();
+    memcpy(d + off, s + off, n - off);
+    while (left.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv.notify_all();
+    for (auto& t : th) if (t.joinable()) t.join();
+  }
+};
+static CopyPool g_copy_pool;
+
+static bool host_pointer_is_pageable(const void* p) {
+  static const int force = getenv("B200_FORCE_STAGING") ? atoi(getenv("B200_FORCE_STAGING")) : 0;
+  if (force) return force > 0;
+  cudaPointerAttributes at;
+  cudaError_t err = cudaPointerGetAttributes(&at, p);
+  if (err != cudaSuccess) { (void)cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+// host -> device copy of `bytes` on stream `cs`; pageable sources go through the pinned ring
+static int h2d_copy(Engine& e, unsigned char* dst, const unsigned char* src, size_t bytes, bool pageable, cudaStream_t cs) {
+  if (!pageable || bytes < (256u << 10)) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs));
+    return E_SUCCESS;
+  }
+  StageRing& r = e.ring;
+  for (size_t off = 0; off < bytes; off += StageRing::SLOT_BYTES) {
+    const size_t len = bytes - off < StageRing::SLOT_BYTES ? bytes - off : StageRing::SLOT_BYTES;
+    const int k = r.next;
+    r.next = (k + 1) % StageRing::SLOTS;
+    if (!r.slot[k]) {
+      CUDA_TRY(cudaMallocHost((void**)&r.slot[k], StageRing::SLOT_BYTES));
+      CUDA_TRY(cudaEventCreateWithFlags(&r.freed[k], cudaEventDisableTiming));
+    }
+    if (r.used[k]) CUDA_TRY(cudaEventSynchronize(r.freed[k]));     // the slot's previous copy has left the host
+    g_copy_pool.copy(r.slot[k], src + off, len);
+    CUDA_TRY(cudaMemcpyAsync(dst + off, r.slot[k], len, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaEventRecord(r.freed[k], cs));
+    r.used[k] = true;
+  }
+  return E_SUCCESS;
 }
 
 // host-resident input: stream it in chunks, copy of chunk i+1 overlapped with accumulation of chunk i.
-// Leaves the XYZZ partial sum in e.partial and the status key in e.status (both on the device), all work
-// queued on e.stream.
+// Leaves the XYZZ partial sum at dst_partial (default e.partial) and the status key in e.status (and a copy at
+// dst_status if given) -- both may be PEER pointers on another GPU --, all work queued on e.stream.
 template <class F>
-static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, uint64_t index_base) {
+static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, uint64_t index_base,
+                                XYZZ<F>* dst_partial = nullptr, unsigned long long* dst_status = nullptr) {
   int rc;
   const size_t pair_bytes = Wire<F>::PAIR_WORDS * 4;
   if ((rc = e.raw.reserve(n * pair_bytes))) return rc;
   if ((rc = e.partial.reserve(sizeof(XYZZ<Fp2>)))) return rc;
   if ((rc = e.status.reserve(8))) return rc;
   cudaStream_t s = e.stream, cs = e.stream2;
+  const bool pageable = host_pointer_is_pageable(in);
   // Chunk boundaries in 32nds of the input.  Geometric sizes: the first copy (which nothing can hide) is small, and
   // every later copy is shorter than the accumulation of the chunk before it.  B200_STREAM_EVEN=1 restores 8 equal chunks.
   static const int even_env = getenv("B200_STREAM_EVEN") ? atoi(getenv("B200_STREAM_EVEN")) : 0;
@@ -357,54 +628,148 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
     if (lo >= hi) continue;
     unsigned char* dst = (unsigned char*)e.raw.ptr + lo * pair_bytes;
     if (nchunks == 1) {
-      CUDA_TRY(cudaMemcpyAsync(dst, in + lo * pair_bytes, (hi - lo) * pair_bytes, cudaMemcpyHostToDevice, s));
+      if ((rc = h2d_copy(e, dst, in + lo * pair_bytes, (hi - lo) * pair_bytes, pageable, s))) return rc;
     } else {
-      CUDA_TRY(cudaMemcpyAsync(dst, in + lo * pair_bytes, (hi - lo) * pair_bytes, cudaMemcpyHostToDevice, cs));
+      if ((rc = h2d_copy(e, dst, in + lo * pair_bytes, (hi - lo) * pair_bytes, pageable, cs))) return rc;
       CUDA_TRY(cudaEventRecord(e.ev_group[c], cs));
       CUDA_TRY(cudaStreamWaitEvent(s, e.ev_group[c], 0));
     }
     if ((rc = msm_feed<F>(e, r, (const uint32_t*)dst, hi - lo, index_base + lo, first, (unsigned long long*)e.status.ptr, s))) return rc;
     first = false;
   }
-  return msm_tail<F>(e, r, (XYZZ<F>*)e.partial.ptr, s);
+  return msm_tail<F>(e, r, dst_partial ? dst_partial : (XYZZ<F>*)e.partial.ptr, (unsigned long long*)e.status.ptr, dst_status, s);
+}
+
+// finish a host call on workspace e: partial sum(s) -> affine -> bytes; `out` is written only on success
+// (eip2537.c:613, :701 encode last)
+template <class F>
+static int msm_finish_host(Engine& e, const ShardRecord* recs, int count, unsigned char* out) {
+  int rc;
+  const size_t out_bytes = Wire<F>::POINT_WORDS * 4;
+  if ((rc = e.out.reserve(out_bytes + 16))) return rc;
+  cudaStream_t s = e.stream;
+  unsigned long long* d_st = (unsigned long long*)((unsigned char*)e.out.ptr + ((out_bytes + 15) & ~(size_t)15));
+  if (recs) {
+    LAUNCH(k_finalize_records<F>, 1, 32, s, recs, count, (uint32_t*)e.out.ptr, d_st);
+  } else {
+    LAUNCH(k_finalize<F>, 1, 32, s, (const XYZZ<F>*)e.partial.ptr, 1, (uint32_t*)e.out.ptr);
+    d_st = (unsigned long long*)e.status.ptr;
+  }
+  CUDA_TRY(cudaMemcpyAsync(e.h_out, e.out.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(e.h_status, d_st, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  unsigned long long st = *e.h_status;
+  if (st != STATUS_OK) return (int)(st & 0xFF);
+  memcpy(out, e.h_out, out_bytes);
+  return E_SUCCESS;
+}
+
+// ---- one process, several GPUs: the plain ABI call shards its pairs -------------------------
+// bls12_b200_init_multi(G) makes a LARGE bls12_g{1,2}multiexp call split its pair range over G devices: one host
+// thread and one stream per device, each device pulls its slice over its own PCIe link and runs the whole
+// single-GPU pipeline; its LAST kernel (k_window_combine) stores the partial sum and the first-error key straight
+// into device 0's gather buffer through NVLink peer memory (the one exchange step: G x 512 B), and device 0 sums,
+// inverts once and encodes.  Error precedence is the minimum (global pair index << 8 | code) over the shards.
+static std::atomic<int> g_ngpu{1};
+static bool g_peer_ok[MAX_DEVICES] = {};
+static constexpr size_t MULTI_MIN_PAIRS_PER_GPU = (size_t)1 << 17;
+
+template <class F>
+static int msm_multi_host(const unsigned char* in, size_t n, unsigned char* out, int G) {
+  Lease l0;
+  int rc = l0.acquire(0);
+  if (rc) return rc;
+  Engine& e0 = *l0.e;
+  if ((rc = e0.gather.reserve((size_t)G * sizeof(ShardRecord)))) return rc;
+  ShardRecord* recs = (ShardRecord*)e0.gather.ptr;
+  const size_t pair_bytes = Wire<F>::PAIR_WORDS * 4;
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  auto shard = [&](int d) {
+    const size_t lo = n * (size_t)d / G, hi = n * (size_t)(d + 1) / G;
+    Lease ld;
+    Engine* e = &e0;
+    if (d != 0) {
+      if ((rcs[d] = ld.acquire(d))) { errs[d] = g_last_error; return; }
+      e = ld.e;
+    }
+    int r;
+    if (d == 0 || g_peer_ok[d]) {
+      r = msm_stream_from_host<F>(*e, in + lo * pair_bytes, hi - lo, lo, (XYZZ<F>*)recs[d].partial, &recs[d].status);
+    } else {   // no peer mapping: stage locally, then a peer copy of the 512-byte record
+      r = e->gather.reserve(sizeof(ShardRecord));
+      ShardRecord* local = (ShardRecord*)e->gather.ptr;
+      if (!r) r = msm_stream_from_host<F>(*e, in + lo * pair_bytes, hi - lo, lo, (XYZZ<F>*)local->partial, &local->status);
+      if (!r && cudaMemcpyPeerAsync(&recs[d], 0, local, d, sizeof(ShardRecord), e->stream) != cudaSuccess) r = E_MEMORY;
+    }
+    if (!r && cudaStreamSynchronize(e->stream) != cudaSuccess) r = E_MEMORY;
+    if (r) { rcs[d] = r; errs[d] = g_last_error; }
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < G; d++) th.emplace_back(shard, d);
+  shard(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < G; d++)
+    if (rcs[d]) { snprintf(g_last_error, sizeof g_last_error, "device %d: %s", d, errs[d].c_str()); return rcs[d]; }
+  return msm_finish_host<F>(e0, recs, G, out);
 }
 
 template <class F>
 static int msm_host_impl(const unsigned char* in, size_t n, unsigned char* out) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  const int ngpu = g_ngpu.load();
+  if (ngpu > 1) {
+    size_t G = n / MULTI_MIN_PAIRS_PER_GPU;
+    if (G > (size_t)ngpu) G = ngpu;
+    if (G > 1) return msm_multi_host<F>(in, n, out, (int)G);
+  }
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
-  int prev;
-  CUDA_TRY(cudaGetDevice(&prev));
-  if (prev != e.device) CUDA_TRY(cudaSetDevice(e.device));
-  const size_t out_bytes = Wire<F>::POINT_WORDS * 4;
-  if ((rc = e.out.reserve(out_bytes))) return rc;
+  Engine& e = *lease.e;
   if ((rc = msm_stream_from_host<F>(e, in, n, 0))) return rc;
-  cudaStream_t s = e.stream;
-  LAUNCH(k_finalize<F>, 1, 32, s, (const XYZZ<F>*)e.partial.ptr, 1, (uint32_t*)e.out.ptr);
-  CUDA_TRY(cudaMemcpyAsync(e.h_out, e.out.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(e.h_status, e.status.ptr, 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  unsigned long long st = *e.h_status;
-  if (st != STATUS_OK) return (int)(st & 0xFF);
-  memcpy(out, e.h_out, out_bytes);   // `out` is written only on success (eip2537.c:613, :701)
-  return E_SUCCESS;
+  return msm_finish_host<F>(e, nullptr, 1, out);
+}
+
+extern "C" EIP2537_ERROR bls12_b200_init_multi(int ngpu) {
+  int count = 0;
+  CUDA_TRY2(cudaGetDeviceCount(&count));
+  if (ngpu <= 0 || ngpu > count) ngpu = count;
+  if (ngpu > MAX_DEVICES) ngpu = MAX_DEVICES;
+  int prev = 0;
+  CUDA_TRY2(cudaGetDevice(&prev));
+  for (int d = 0; d < ngpu; d++) {
+    DevicePool* p;
+    int rc = pool_get(&p, d);
+    if (rc) return (EIP2537_ERROR)rc;
+    if (d == 0) continue;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, d, 0) != cudaSuccess) { (void)cudaGetLastError(); can = 0; }
+    if (can) {
+      CUDA_TRY2(cudaSetDevice(d));
+      cudaError_t err = cudaDeviceEnablePeerAccess(0, 0);
+      if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+      (void)cudaGetLastError();
+    }
+    g_peer_ok[d] = can != 0;
+  }
+  CUDA_TRY2(cudaSetDevice(prev));
+  g_ngpu.store(ngpu);
+  return EIP2537_SUCCESS;
+}
+extern "C" int bls12_b200_multi_gpus(void) { return g_ngpu.load(); }
+extern "C" uint64_t bls12_b200_device_launch_count(int device) {
+  return device >= 0 && device < MAX_DEVICES ? g_pools[device].launches.load() : 0;
 }
 
 // multi-GPU sharding with host-resident shards: stream this rank's slice in, leave the partial sum and
-// the status key in caller-provided DEVICE buffers (ready for the NCCL all-gather); synchronous
+// the status key in caller-provided DEVICE buffers (ready for an all-gather); synchronous
 template <class F>
 static int msm_partial_host_impl(const unsigned char* in, size_t n, uint64_t index_base, void* d_partial, uint64_t* d_status) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
-  if ((rc = msm_stream_from_host<F>(e, in, n, index_base))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(d_partial, e.partial.ptr, sizeof(XYZZ<F>), cudaMemcpyDeviceToDevice, e.stream));
-  CUDA_TRY(cudaMemcpyAsync(d_status, e.status.ptr, 8, cudaMemcpyDeviceToDevice, e.stream));
+  Engine& e = *lease.e;
+  if ((rc = msm_stream_from_host<F>(e, in, n, index_base, (XYZZ<F>*)d_partial, (unsigned long long*)d_status))) return rc;
   CUDA_TRY(cudaStreamSynchronize(e.stream));
   return E_SUCCESS;
 }
@@ -419,20 +784,25 @@ extern "C" int b200_msm_host(int group, const unsigned char* in, size_t n, unsig
   return group == 1 ? msm_host_impl<Fp>(in, n, out) : msm_host_impl<Fp2>(in, n, out);
 }
 
-template <class F>
-static int msm_partial_device_impl(const void* d_in, size_t n, uint64_t index_base, void* d_partial,
-                                   uint64_t* d_status, void* stream) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
-  if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (((uintptr_t)d_in & 15) || ((uintptr_t)d_partial & 15)) {
+static int check_device_args(const void* a, const void* b) {
+  if (((uintptr_t)a & 15) || ((uintptr_t)b & 15)) {
     snprintf(g_last_error, sizeof g_last_error, "device pointers must be 16-byte aligned");
     return E_MEMORY;
   }
-  return msm_pipeline<F>(e, (const uint32_t*)d_in, n, index_base, (XYZZ<F>*)d_partial, (unsigned long long*)d_status, s);
+  return E_SUCCESS;
+}
+
+template <class F>
+static int msm_partial_device_impl(const void* d_in, size_t n, uint64_t index_base, void* d_partial,
+                                   uint64_t* d_status, void* stream) {
+  int rc = check_device_args(d_in, d_partial);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  Lease lease;
+  if ((rc = lease.acquire(-1, true, s))) return rc;
+  rc = msm_pipeline<F>(*lease.e, (const uint32_t*)d_in, n, index_base, (XYZZ<F>*)d_partial, (unsigned long long*)d_status, nullptr, s);
+  lease.submitted(s);
+  return rc;
 }
 
 extern "C" EIP2537_ERROR bls12_b200_msm_partial_device(int group, const void* d_in, size_t n, uint64_t index_base,
@@ -444,31 +814,176 @@ extern "C" EIP2537_ERROR bls12_b200_msm_partial_device(int group, const void* d_
 
 extern "C" EIP2537_ERROR bls12_b200_msm_combine_device(int group, const void* d_partials, int count, void* d_out,
                                                        void* stream) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  DevicePool* p;
+  int rc = pool_get(&p, -1);
   if (rc) return (EIP2537_ERROR)rc;
+  (void)cudaGetLastError();
   cudaStream_t s = (cudaStream_t)stream;
   if (group == 1) LAUNCH(k_finalize<Fp>, 1, 32, s, (const XYZZ<Fp>*)d_partials, count, (uint32_t*)d_out);
   else            LAUNCH(k_finalize<Fp2>, 1, 32, s, (const XYZZ<Fp2>*)d_partials, count, (uint32_t*)d_out);
-  if (cudaGetLastError() != cudaSuccess) return EIP2537_MEMORY_ERROR;
+  CUDA_TRY2(cudaGetLastError());
   return EIP2537_SUCCESS;
 }
 
+template <class F>
+static int msm_device_impl(const void* d_in, size_t n, void* d_out, uint64_t* d_status, cudaStream_t s) {
+  int rc = check_device_args(d_in, d_out);
+  if (rc) return rc;
+  Lease lease;
+  if ((rc = lease.acquire(-1, true, s))) return rc;
+  Engine& e = *lease.e;
+  if ((rc = e.partial.reserve(sizeof(XYZZ<Fp2>)))) return rc;      // the partial sum lives in THIS submission's workspace
+  CUDA_TRY(cudaMemsetAsync(d_status, 0xFF, 8, s));
+  rc = msm_pipeline<F>(e, (const uint32_t*)d_in, n, 0, (XYZZ<F>*)e.partial.ptr, (unsigned long long*)d_status, nullptr, s);
+  if (!rc) {
+    LAUNCH(k_finalize<F>, 1, 32, s, (const XYZZ<F>*)e.partial.ptr, 1, (uint32_t*)d_out);
+    if (cudaGetLastError() != cudaSuccess) rc = E_MEMORY;
+  }
+  lease.submitted(s);
+  return rc;
+}
 extern "C" EIP2537_ERROR bls12_b200_msm_device(int group, const void* d_in, size_t n, void* d_out,
                                                uint64_t* d_status, void* stream) {
   if (n == 0) return EIP2537_INVALID_LENGTH;
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
-  if (rc) return (EIP2537_ERROR)rc;
-  {
-    std::lock_guard<std::mutex> lk(ep->mu);
-    if ((rc = ep->partial.reserve(sizeof(XYZZ<Fp2>)))) return (EIP2537_ERROR)rc;
+  return (EIP2537_ERROR)(group == 1 ? msm_device_impl<Fp>(d_in, n, d_out, d_status, (cudaStream_t)stream)
+                                    : msm_device_impl<Fp2>(d_in, n, d_out, d_status, (cudaStream_t)stream));
+}
+
+// ---- one process PER GPU (torchrun / MPI style): the exchange is ONE ncclAllGather issued from here ----------
+// NCCL is loaded lazily with dlopen (libnccl.so.2, or B200_NCCL_LIB), so single-GPU consumers of the library
+// (the Go / Rust packages) carry no NCCL dependency.
+namespace nccl_dl {
+typedef struct ncclComm* comm_t;
+struct unique_id { char internal[128]; };
+typedef int (*get_unique_id_fn)(unique_id*);
+typedef int (*comm_init_rank_fn)(comm_t*, int, unique_id, int);
+typedef int (*all_gather_fn)(const void*, void*, size_t, int, comm_t, cudaStream_t);
+typedef int (*comm_destroy_fn)(comm_t);
+typedef const char* (*get_error_string_fn)(int);
+static void* handle = nullptr;
+static get_unique_id_fn get_unique_id = nullptr;
+static comm_init_rank_fn comm_init_rank = nullptr;
+static all_gather_fn all_gather = nullptr;
+static comm_destroy_fn comm_destroy = nullptr;
+static get_error_string_fn get_error_string = nullptr;
+static comm_t comm = nullptr;
+static int world = 1, rank = 0;
+static std::mutex mu;
+static int load() {
+  std::lock_guard<std::mutex> lk(mu);
+  if (handle) return E_SUCCESS;
+  const char* names[] = {getenv("B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm) continue;
+    handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (handle) break;
   }
-  cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(d_status, 0xFF, 8, s) != cudaSuccess) return EIP2537_MEMORY_ERROR;
-  EIP2537_ERROR r = bls12_b200_msm_partial_device(group, d_in, n, 0, ep->partial.ptr, d_status, (void*)s);
-  if (r) return r;
-  return bls12_b200_msm_combine_device(group, ep->partial.ptr, 1, d_out, (void*)s);
+  if (!handle) { snprintf(g_last_error, sizeof g_last_error, "NCCL not found: %s", dlerror()); return E_MEMORY; }
+  get_unique_id = (get_unique_id_fn)dlsym(handle, "ncclGetUniqueId");
+  comm_init_rank = (comm_init_rank_fn)dlsym(handle, "ncclCommInitRank");
+  all_gather = (all_gather_fn)dlsym(handle, "ncclAllGather");
+  comm_destroy = (comm_destroy_fn)dlsym(handle, "ncclCommDestroy");
+  get_error_string = (get_error_string_fn)dlsym(handle, "ncclGetErrorString");
+  if (!get_unique_id || !comm_init_rank || !all_gather || !comm_destroy) {
+    snprintf(g_last_error, sizeof g_last_error, "NCCL symbols missing");
+    handle = nullptr;
+    return E_MEMORY;
+  }
+  return E_SUCCESS;
+}
+static int fail(const char* what, int code) {
+  snprintf(g_last_error, sizeof g_last_error, "%s: %s", what, get_error_string ? get_error_string(code) : "nccl error");
+  return E_MEMORY;
+}
+}  // namespace nccl_dl
+
+extern "C" EIP2537_ERROR bls12_b200_comm_unique_id(byte* id128) {
+  int rc = nccl_dl::load();
+  if (rc) return (EIP2537_ERROR)rc;
+  nccl_dl::unique_id id;
+  int r = nccl_dl::get_unique_id(&id);
+  if (r) return (EIP2537_ERROR)nccl_dl::fail("ncclGetUniqueId", r);
+  memcpy(id128, &id, 128);
+  return EIP2537_SUCCESS;
+}
+extern "C" EIP2537_ERROR bls12_b200_comm_init(int world, int rank, const byte* id128) {
+  int rc = nccl_dl::load();
+  if (rc) return (EIP2537_ERROR)rc;
+  DevicePool* p;
+  if ((rc = pool_get(&p, -1))) return (EIP2537_ERROR)rc;
+  nccl_dl::unique_id id;
+  memcpy(&id, id128, 128);
+  if (nccl_dl::comm) { nccl_dl::comm_destroy(nccl_dl::comm); nccl_dl::comm = nullptr; }
+  int r = nccl_dl::comm_init_rank(&nccl_dl::comm, world, id, rank);
+  if (r) return (EIP2537_ERROR)nccl_dl::fail("ncclCommInitRank", r);
+  nccl_dl::world = world; nccl_dl::rank = rank;
+  return EIP2537_SUCCESS;
+}
+extern "C" void bls12_b200_comm_destroy(void) {
+  if (nccl_dl::comm) { nccl_dl::comm_destroy(nccl_dl::comm); nccl_dl::comm = nullptr; }
+  nccl_dl::world = 1; nccl_dl::rank = 0;
+}
+
+// this rank's shard -> record {partial, status} -> ONE all-gather of world x 512 B -> every rank sums, inverts, encodes
+template <class F>
+static int msm_sharded_finish(Engine& e, uint32_t* d_out, unsigned long long* d_status, cudaStream_t s) {
+  ShardRecord* recs = (ShardRecord*)e.gather.ptr;     // [0] = this rank's record, [1 .. world] = gathered
+  if (nccl_dl::world > 1) {
+    if (!nccl_dl::comm) { snprintf(g_last_error, sizeof g_last_error, "bls12_b200_comm_init was not called"); return E_MEMORY; }
+    int r = nccl_dl::all_gather(recs, recs + 1, sizeof(ShardRecord), /*ncclUint8*/ 1, nccl_dl::comm, s);
+    if (r) return nccl_dl::fail("ncclAllGather", r);
+    LAUNCH(k_finalize_records<F>, 1, 32, s, recs + 1, nccl_dl::world, d_out, d_status);
+  } else {
+    LAUNCH(k_finalize_records<F>, 1, 32, s, recs, 1, d_out, d_status);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return E_SUCCESS;
+}
+template <class F>
+static int msm_sharded_device_impl(const void* d_in, size_t n, uint64_t index_base, void* d_out, uint64_t* d_status, cudaStream_t s) {
+  int rc = check_device_args(d_in, d_out);
+  if (rc) return rc;
+  Lease lease;
+  if ((rc = lease.acquire(-1, true, s))) return rc;
+  Engine& e = *lease.e;
+  if ((rc = e.gather.reserve((size_t)(nccl_dl::world + 1) * sizeof(ShardRecord)))) return rc;
+  ShardRecord* recs = (ShardRecord*)e.gather.ptr;
+  if ((rc = e.status.reserve(8))) return rc;
+  CUDA_TRY(cudaMemsetAsync(e.status.ptr, 0xFF, 8, s));
+  rc = msm_pipeline<F>(e, (const uint32_t*)d_in, n, index_base, (XYZZ<F>*)recs[0].partial, (unsigned long long*)e.status.ptr, &recs[0].status, s);
+  if (!rc) rc = msm_sharded_finish<F>(e, (uint32_t*)d_out, (unsigned long long*)d_status, s);
+  lease.submitted(s);
+  return rc;
+}
+extern "C" EIP2537_ERROR bls12_b200_msm_sharded_device(int group, const void* d_in, size_t n, uint64_t index_base, void* d_out,
+                                                       uint64_t* d_status, void* stream) {
+  if (n == 0) return EIP2537_INVALID_LENGTH;
+  return (EIP2537_ERROR)(group == 1 ? msm_sharded_device_impl<Fp>(d_in, n, index_base, d_out, d_status, (cudaStream_t)stream)
+                                    : msm_sharded_device_impl<Fp2>(d_in, n, index_base, d_out, d_status, (cudaStream_t)stream));
+}
+template <class F>
+static int msm_sharded_host_impl(const unsigned char* in, size_t n, uint64_t index_base, unsigned char* out) {
+  Lease lease;
+  int rc = lease.acquire(-1);
+  if (rc) return rc;
+  Engine& e = *lease.e;
+  const size_t out_bytes = Wire<F>::POINT_WORDS * 4;
+  if ((rc = e.gather.reserve((size_t)(nccl_dl::world + 1) * sizeof(ShardRecord)))) return rc;
+  if ((rc = e.out.reserve(out_bytes + 16))) return rc;
+  ShardRecord* recs = (ShardRecord*)e.gather.ptr;
+  unsigned long long* d_st = (unsigned long long*)((unsigned char*)e.out.ptr + ((out_bytes + 15) & ~(size_t)15));
+  if ((rc = msm_stream_from_host<F>(e, in, n, index_base, (XYZZ<F>*)recs[0].partial, &recs[0].status))) return rc;
+  if ((rc = msm_sharded_finish<F>(e, (uint32_t*)e.out.ptr, d_st, e.stream))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(e.h_out, e.out.ptr, out_bytes, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaMemcpyAsync(e.h_status, d_st, 8, cudaMemcpyDeviceToHost, e.stream));
+  CUDA_TRY(cudaStreamSynchronize(e.stream));
+  if (*e.h_status != STATUS_OK) return (int)(*e.h_status & 0xFF);
+  memcpy(out, e.h_out, out_bytes);
+  return E_SUCCESS;
+}
+extern "C" EIP2537_ERROR bls12_b200_msm_sharded_host(int group, const byte* in, size_t n, uint64_t index_base, byte* out) {
+  if (n == 0) return EIP2537_INVALID_LENGTH;
+  return (EIP2537_ERROR)(group == 1 ? msm_sharded_host_impl<Fp>(in, n, index_base, out) : msm_sharded_host_impl<Fp2>(in, n, index_base, out));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -476,11 +991,10 @@ extern "C" EIP2537_ERROR bls12_b200_msm_device(int group, const void* d_in, size
 // ------------------------------------------------------------------------------------------
 template <class F>
 static int msm_batch_impl(unsigned char* outs, int* errs, const unsigned char* in, const uint64_t* offsets, size_t n) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
+  Engine& e = *lease.e;
   constexpr size_t PAIR = Wire<F>::PAIR_WORDS * 4, OUT = Wire<F>::POINT_WORDS * 4;
   // calls with a bad length contribute no pairs (answered INVALID_LENGTH, eip2537.c:543 / :831)
   std::vector<unsigned long long> off(n + 1);
@@ -550,11 +1064,10 @@ __global__ void k_add_points(const uint32_t* __restrict__ raw, uint32_t* __restr
 
 template <class F>
 static int add_host_impl(const unsigned char* in, unsigned char* out) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
+  Engine& e = *lease.e;
   const size_t in_bytes = 2 * Wire<F>::POINT_WORDS * 4, out_bytes = Wire<F>::POINT_WORDS * 4;
   if ((rc = e.raw.reserve(in_bytes))) return rc;
   if ((rc = e.out.reserve(out_bytes))) return rc;
@@ -581,11 +1094,10 @@ extern "C" int b200_add_host(int group, const unsigned char* in, unsigned char* 
 template <class F>
 static int map_host_impl(unsigned char* outs, int* codes, const unsigned char* in, size_t n) {
   if (n == 0) return E_SUCCESS;
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
+  Engine& e = *lease.e;
   const size_t in_bytes = n * (Wire<F>::POINT_WORDS * 2), out_bytes = n * (Wire<F>::POINT_WORDS * 4);
   if ((rc = e.raw.reserve(in_bytes))) return rc;
   if ((rc = e.pts.reserve(out_bytes))) return rc;
@@ -640,11 +1152,10 @@ __global__ void __launch_bounds__(128) k_generator_mul(const uint32_t* __restric
 
 template <class F>
 static int generator_mul_impl(unsigned char* out, const unsigned char* scalars, size_t n) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
+  Engine& e = *lease.e;
   const size_t out_bytes = n * Wire<F>::POINT_WORDS * 4;
   if ((rc = e.raw.reserve(32 * n))) return rc;
   if ((rc = e.pts.reserve(out_bytes))) return rc;
@@ -665,30 +1176,46 @@ extern "C" EIP2537_ERROR bls12_b200_g2_generator_mul(byte* out, const byte* scal
 // ------------------------------------------------------------------------------------------
 // pairing
 // ------------------------------------------------------------------------------------------
+static std::atomic<const PairingPlanState*> g_last_plan{nullptr};
+static std::atomic<int> g_last_plan_device{0};
+
 static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const unsigned long long* d_offsets, size_t n_calls,
                                      size_t total_pairs, uint32_t* d_outs, int* d_errs, cudaStream_t s) {
   int rc;
   const size_t max_tasks = total_pairs;    // every chunk holds at least one pair
   if (total_pairs > (4u << 20)) { snprintf(g_last_error, sizeof g_last_error, "pairing batch too large: split it"); return E_MEMORY; }
+  constexpr size_t PLAN_BYTES = 2048;
+  static_assert(sizeof(PairingPlanState) <= PLAN_BYTES, "plan header");
   if ((rc = e.pr_g1.reserve(total_pairs * sizeof(G1Affine)))) return rc;
   if ((rc = e.pr_g2.reserve(total_pairs * sizeof(G2Affine)))) return rc;
   if ((rc = e.pr_status.reserve(total_pairs * sizeof(int) + total_pairs + 64))) return rc;
   if ((rc = e.pr_lines.reserve((size_t)ML_STEPS * total_pairs * sizeof(Line)))) return rc;
-  if ((rc = e.pr_tasks.reserve(512 + max_tasks * sizeof(PairingTask) + n_calls * sizeof(uint32_t) + 64))) return rc;
+  if ((rc = e.pr_tasks.reserve(PLAN_BYTES + max_tasks * sizeof(PairingTask) + n_calls * sizeof(uint32_t) + 64))) return rc;
   if ((rc = e.pr_f.reserve(max_tasks * sizeof(Fp12)))) return rc;
+  if ((rc = e.pr_slots.reserve(total_pairs * sizeof(uint32_t) + total_pairs + 64))) return rc;
   G1Affine* g1 = (G1Affine*)e.pr_g1.ptr;
   G2Affine* g2 = (G2Affine*)e.pr_g2.ptr;
   int* pstat = (int*)e.pr_status.ptr;
   unsigned char* skip = (unsigned char*)(pstat + total_pairs);
   Line* lines = (Line*)e.pr_lines.ptr;
   PairingPlanState* plan_state = (PairingPlanState*)e.pr_tasks.ptr;
-  PairingTask* tasks = (PairingTask*)((char*)e.pr_tasks.ptr + 512);
+  PairingTask* tasks = (PairingTask*)((char*)e.pr_tasks.ptr + PLAN_BYTES);
   uint32_t* call_first = (uint32_t*)(tasks + max_tasks);
   Fp12* f = (Fp12*)e.pr_f.ptr;
+  uint32_t* slot_pair = (uint32_t*)e.pr_slots.ptr;
+  unsigned char* skip_slot = (unsigned char*)(slot_pair + total_pairs);
   // Pairs per chunk: chosen on the device from the batch's own shape (pairing_choose_chunk); B200_PAIRING_CHUNK forces it.
   static const int forced_chunk = getenv("B200_PAIRING_CHUNK") ? atoi(getenv("B200_PAIRING_CHUNK")) : 0;
-  const uint32_t wave = (uint32_t)e.sm_count * 6 * 64;      // resident threads of k_pairing_accumulate: 6 blocks of 64 per SM
+  // B200_PAIRING_ACC=thread selects round 1's thread-per-chunk accumulate (Fp12 in thread-local memory) for A/B runs
+  static const bool use_dot = !(getenv("B200_PAIRING_ACC") && !strcmp(getenv("B200_PAIRING_ACC"), "thread"));
+  const uint32_t wave_thread = (uint32_t)e.sm_count * 6 * 64;                     // k_pairing_accumulate: 6 blocks of 64 threads per SM
+  static const int dot_blocks = getenv("B200_DOT_BLOCKS") ? atoi(getenv("B200_DOT_BLOCKS")) : DOT_BLOCKS_PER_SM;
+  // B200_DOT_WAVE_PCT: the planner's idea of "one wave" as a percentage of the resident chunk slots (developer sweep)
+  static const int wave_pct = getenv("B200_DOT_WAVE_PCT") ? atoi(getenv("B200_DOT_WAVE_PCT")) : 100;
+  const uint32_t wave_dot = (uint32_t)((uint64_t)e.sm_count * (dot_blocks == 5 ? 5 : 6) * 32 * wave_pct / 100);   // 32 chunks per block
+  const uint32_t fc = (uint32_t)(forced_chunk > 0 ? forced_chunk : 0);
   CUDA_TRY(cudaMemsetAsync(plan_state, 0, sizeof(PairingPlanState), s));
+  g_last_plan.store(plan_state); g_last_plan_device.store(e.device);
   g_pstage.mark(0, s);
   const bool small_batch = (long)n_calls <= g_pairing_coop_max.load();
   if (small_batch) {
@@ -697,30 +1224,38 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
     LAUNCH(k_pairing_decode, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
   }
   g_pstage.mark(1, s);
-  LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
-  g_pstage.mark(2, s);
-  LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs);
-  // Two back ends for "multiply the lines into f, final exponentiation, is-one":
-  //   warp-cooperative (coop12.cuh): one warp per call, Fp12 in shared memory -- low latency, all pairs of a
-  //     call share the squarings;
-  //   thread-per-chunk / thread-per-call (pairing.cuh).
-  //   Measured crossover on B200 (profiles/r01_bench.md): the warp path wins below ~300 calls.
+  // Back ends for "multiply the lines into f, final exponentiation, is-one":
+  //   warp-cooperative (coop12.cuh): one warp per call, Fp12 in shared memory -- lowest latency, small batches;
+  //   dot engine (pairing_dot.cuh): three lanes per chunk, Fp12 in shared memory, one reduction per output
+  //     component -- the throughput path;
+  //   thread-per-chunk (pairing.cuh, round 1): kept for small batches of long calls and for A/B measurements.
   //   A lone warp walks its call's pairs one after the other (~0.55 ms per pair), so small batches of LONG calls
   //   (more than ~12 pairs per call) accumulate per chunk in parallel first and give the warp only the product of
   //   the chunk values and the final exponentiation.
   if (small_batch && total_pairs <= 12 * n_calls) {
+    LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
+    g_pstage.mark(2, s);
+    LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs, (uint32_t)1);
     g_pstage.mark(3, s);
     LAUNCH(k_pairing_call_coop, (unsigned)n_calls, 32, s, n_calls, d_offsets, lines, skip, total_pairs, d_outs, d_errs);
-  } else if (small_batch) {
-    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave, (uint32_t)(forced_chunk > 0 ? forced_chunk : 0),
-           plan_state, tasks, call_first);
+  } else if (!use_dot || small_batch) {
+    LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
+    g_pstage.mark(2, s);
+    LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs, (uint32_t)PAIRING_MAX_CHUNK_THREAD);
+    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave_thread, fc, (uint32_t)PAIRING_MAX_CHUNK_THREAD,
+           plan_state, tasks, call_first, (uint32_t*)nullptr);
     LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, plan_state, lines, skip, total_pairs, f);
     g_pstage.mark(3, s);
-    LAUNCH(k_pairing_call_coop_chunks, (unsigned)n_calls, 32, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
+    if (small_batch) LAUNCH(k_pairing_call_coop_chunks, (unsigned)n_calls, 32, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
+    else             LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
   } else {
-    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave, (uint32_t)(forced_chunk > 0 ? forced_chunk : 0),
-           plan_state, tasks, call_first);
-    LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, plan_state, lines, skip, total_pairs, f);
+    LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs, (uint32_t)PAIRING_MAX_CHUNK);
+    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave_dot, fc, (uint32_t)PAIRING_MAX_CHUNK,
+           plan_state, tasks, call_first, slot_pair);
+    LAUNCH(k_pairing_lines_slots, blocks_for(total_pairs, 64), 64, s, g1, g2, plan_state, slot_pair, total_pairs, (uint32_t*)lines, skip_slot);
+    g_pstage.mark(2, s);
+    if (dot_blocks == 5) LAUNCH_SMEM(k_pairing_accumulate_dot<5>, blocks_for(max_tasks, 32), 96, DOT_SMEM_BYTES, s, tasks, plan_state, (const uint32_t*)lines, skip_slot, total_pairs, f);
+    else                 LAUNCH_SMEM(k_pairing_accumulate_dot<6>, blocks_for(max_tasks, 32), 96, DOT_SMEM_BYTES, s, tasks, plan_state, (const uint32_t*)lines, skip_slot, total_pairs, f);
     g_pstage.mark(3, s);
     LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
   }
@@ -729,77 +1264,104 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   return E_SUCCESS;
 }
 
+// pairs per chunk the planner chose for the last pairing batch (bench.py: algorithmic work of the accumulate kernel)
+extern "C" int bls12_b200_last_pairing_chunk(void) {
+  const PairingPlanState* p = g_last_plan.load();
+  if (!p) return 0;
+  uint32_t chunk = 0;
+  if (cudaMemcpy(&chunk, &p->chunk, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return (int)chunk;
+}
+
 extern "C" EIP2537_ERROR bls12_b200_pairing_batch_device(const void* d_in, const uint64_t* d_offsets, size_t n,
                                                          size_t total_pairs, void* d_outs, int32_t* d_errs, void* stream) {
   if (n == 0) return EIP2537_SUCCESS;
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
-  if (rc) return (EIP2537_ERROR)rc;
-  std::lock_guard<std::mutex> lk(ep->mu);
   cudaStream_t s = (cudaStream_t)stream;
-  return (EIP2537_ERROR)pairing_batch_device_impl(*ep, (const uint32_t*)d_in, (const unsigned long long*)d_offsets, n,
-                                                  total_pairs, (uint32_t*)d_outs, (int*)d_errs, s);
+  Lease lease;
+  int rc = lease.acquire(-1, true, s);
+  if (rc) return (EIP2537_ERROR)rc;
+  rc = pairing_batch_device_impl(*lease.e, (const uint32_t*)d_in, (const unsigned long long*)d_offsets, n,
+                                 total_pairs, (uint32_t*)d_outs, (int*)d_errs, s);
+  lease.submitted(s);
+  return (EIP2537_ERROR)rc;
 }
 
-extern "C" EIP2537_ERROR bls12_pairing_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, const uint64_t* offsets, size_t n) {
-  if (n == 0) return EIP2537_SUCCESS;
+// n independent calls on ONE device (device < 0: the current one); host buffers, synchronous
+static int pairing_batch_on_device(int device, unsigned char* outs, int* errs, const unsigned char* in, const uint64_t* offsets, size_t n) {
   // per-call length validation on the host (eip2537.c:1022-1024); bad calls become zero-pair calls on the device
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
-  if (rc) return (EIP2537_ERROR)rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
-  int prev;
-  CUDA_TRY2(cudaGetDevice(&prev));
-  if (prev != e.device) CUDA_TRY2(cudaSetDevice(e.device));
+  Lease lease;
+  int rc = lease.acquire(device);
+  if (rc) return rc;
+  Engine& e = *lease.e;
   const size_t total_bytes = (size_t)(offsets[n] - offsets[0]);
-  size_t total_pairs = 0;
-  // compacted offsets: calls with an invalid length contribute no pairs
-  unsigned long long* h_off = (unsigned long long*)malloc((n + 1) * sizeof(unsigned long long));
-  if (!h_off) return EIP2537_MEMORY_ERROR;
+  size_t total_pairs = 0, cursor = 0;
+  std::vector<unsigned long long> h_off(n + 1);      // compacted offsets: calls with an invalid length contribute no pairs
   bool any_bad = false;
   for (size_t i = 0; i < n; i++) {
     size_t len = (size_t)(offsets[i + 1] - offsets[i]);
-    if (len == 0 || len % 384) any_bad = true;
-  }
-  // simple path: device wants every call well-formed; malformed calls are answered here
-  size_t cursor = 0;
-  for (size_t i = 0; i < n; i++) {
-    size_t len = (size_t)(offsets[i + 1] - offsets[i]);
     h_off[i] = cursor;
-    if (!(len == 0 || len % 384)) { cursor += len; total_pairs += len / 384; }
+    if (len == 0 || len % 384) any_bad = true;
+    else { cursor += len; total_pairs += len / 384; }
   }
   h_off[n] = cursor;
   cudaStream_t s = e.stream;
   if ((rc = e.pr_raw.reserve(cursor + 16)) || (rc = e.pr_offsets.reserve((n + 1) * 8)) ||
-      (rc = e.pr_outs.reserve(n * 32)) || (rc = e.pr_errs.reserve(n * 4))) { free(h_off); return (EIP2537_ERROR)rc; }
-  cudaError_t ce = cudaSuccess;
+      (rc = e.pr_outs.reserve(n * 32)) || (rc = e.pr_errs.reserve(n * 4))) return rc;
+  const bool pageable = host_pointer_is_pageable(in);
   if (!any_bad) {
-    ce = cudaMemcpyAsync(e.pr_raw.ptr, in + offsets[0], total_bytes, cudaMemcpyHostToDevice, s);
+    if ((rc = h2d_copy(e, (unsigned char*)e.pr_raw.ptr, in + offsets[0], total_bytes, pageable, s))) return rc;
   } else {
-    for (size_t i = 0; i < n && ce == cudaSuccess; i++) {
+    for (size_t i = 0; i < n; i++) {
       size_t len = (size_t)(h_off[i + 1] - h_off[i]);
-      if (len) ce = cudaMemcpyAsync((char*)e.pr_raw.ptr + h_off[i], in + offsets[i], len, cudaMemcpyHostToDevice, s);
+      if (len) CUDA_TRY(cudaMemcpyAsync((char*)e.pr_raw.ptr + h_off[i], in + offsets[i], len, cudaMemcpyHostToDevice, s));
     }
   }
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(e.pr_offsets.ptr, h_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
-  if (ce != cudaSuccess) { free(h_off); snprintf(g_last_error, sizeof g_last_error, "H2D: %s", cudaGetErrorString(ce)); return EIP2537_MEMORY_ERROR; }
-  rc = total_pairs ? pairing_batch_device_impl(e, (const uint32_t*)e.pr_raw.ptr, (const unsigned long long*)e.pr_offsets.ptr, n,
-                                               total_pairs, (uint32_t*)e.pr_outs.ptr, (int*)e.pr_errs.ptr, s)
-                   : E_SUCCESS;
-  if (rc) { free(h_off); return (EIP2537_ERROR)rc; }
+  CUDA_TRY(cudaMemcpyAsync(e.pr_offsets.ptr, h_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
   if (total_pairs) {
-    ce = cudaMemcpyAsync(outs, e.pr_outs.ptr, n * 32, cudaMemcpyDeviceToHost, s);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(errs, e.pr_errs.ptr, n * 4, cudaMemcpyDeviceToHost, s);
+    if ((rc = pairing_batch_device_impl(e, (const uint32_t*)e.pr_raw.ptr, (const unsigned long long*)e.pr_offsets.ptr, n,
+                                        total_pairs, (uint32_t*)e.pr_outs.ptr, (int*)e.pr_errs.ptr, s))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(outs, e.pr_outs.ptr, n * 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(errs, e.pr_errs.ptr, n * 4, cudaMemcpyDeviceToHost, s));
   }
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-  if (ce != cudaSuccess) { free(h_off); snprintf(g_last_error, sizeof g_last_error, "pairing: %s", cudaGetErrorString(ce)); return EIP2537_MEMORY_ERROR; }
+  CUDA_TRY(cudaStreamSynchronize(s));          // h_off and the caller's buffers stay alive until here
   for (size_t i = 0; i < n; i++) {
     size_t len = (size_t)(offsets[i + 1] - offsets[i]);
     if (len == 0 || len % 384) { errs[i] = EIP2537_INVALID_LENGTH; memset(outs + 32 * i, 0, 32); }
     else if (errs[i] != EIP2537_SUCCESS) memset(outs + 32 * i, 0, 32);
   }
-  free(h_off);
+  return E_SUCCESS;
+}
+
+// Calls are independent units: after bls12_b200_init_multi(G) a large batch is cut into G contiguous groups of calls
+// (balanced by pair count), one host thread per device, no collective.
+extern "C" EIP2537_ERROR bls12_pairing_batch(byte* outs, EIP2537_ERROR* errs, const byte* in, const uint64_t* offsets, size_t n) {
+  if (n == 0) return EIP2537_SUCCESS;
+  int G = g_ngpu.load();
+  if ((size_t)G > n / 256) G = (int)(n / 256);
+  if (G <= 1) return (EIP2537_ERROR)pairing_batch_on_device(-1, outs, (int*)errs, in, offsets, n);
+  std::vector<size_t> cut(G + 1, n);
+  cut[0] = 0;
+  const uint64_t total = offsets[n] - offsets[0];
+  for (int d = 1; d < G; d++) {          // first call whose start is past d/G of the bytes
+    const uint64_t want = offsets[0] + total * d / G;
+    size_t lo = cut[d - 1], hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (offsets[mid] < want) lo = mid + 1; else hi = mid; }
+    cut[d] = lo;
+  }
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> msgs(G);
+  auto work = [&](int d) {
+    const size_t lo = cut[d], hi = cut[d + 1];
+    if (lo >= hi) return;
+    rcs[d] = pairing_batch_on_device(d, outs + 32 * lo, (int*)errs + lo, in, offsets + lo, hi - lo);
+    if (rcs[d]) msgs[d] = g_last_error;
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < G; d++) th.emplace_back(work, d);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < G; d++)
+    if (rcs[d]) { snprintf(g_last_error, sizeof g_last_error, "device %d: %s", d, msgs[d].c_str()); return (EIP2537_ERROR)rcs[d]; }
   return EIP2537_SUCCESS;
 }
 
@@ -897,11 +1459,10 @@ __global__ void __launch_bounds__(256) k_imad_carry_probe(int iters, unsigned lo
 }
 
 extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return (EIP2537_ERROR)rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
+  Engine& e = *lease.e;
   unsigned nblk = blocks_for(n_threads, 256);
   if ((rc = e.pts.reserve((size_t)nblk * sizeof(Fp)))) return (EIP2537_ERROR)rc;
   cudaEvent_t t0, t1;
@@ -967,17 +1528,30 @@ __global__ void __launch_bounds__(128) k_selftest(size_t n, unsigned long long* 
     Fp a2 = (i & 8) ? pm1 : a, b2 = (i & 16) ? pm1 : b;
     if (!eq(mul_diff(a2, b2, c2, d2), sub(mul_portable(a2, b2), mul_portable(c2, d2)))) atomicAdd(&mismatches[0], 1ull);
   }
+  {  // dot engine (dot12.cuh): 1..12 double-width products accumulated, ONE reduction, against the sum of portable products
+    Fp pm1 = fp_load_const(C_P()); pm1.v[0] -= 1;
+    dot::Acc A;
+    dot::acc_zero(A);
+    Fp sum = fp_zero(), aa = a, bb = b;
+    const int nt = 1 + (int)(i % 12);
+    for (int t = 0; t < nt; t++) {
+      if ((i & 31) == 7) { aa = pm1; bb = pm1; }
+      dot::acc_product(A, aa, bb);
+      sum = add(sum, mul_portable(aa, bb));
+      aa = add(aa, b); bb = sub(bb, a);
+    }
+    if (!eq(dot::acc_reduce(A, nt > 9 ? 2 : 1), sum)) atomicAdd(&mismatches[0], 1ull);
+  }
   if (!eq(add(a, b), st_add_ref(a, b, false))) atomicAdd(&mismatches[1], 1ull);
   if (!eq(sub(a, b), st_add_ref(a, b, true))) atomicAdd(&mismatches[2], 1ull);
   Fp q = mul(a, b);
   if (!is_zero(a) && !is_zero(b) && (i & 63) == 5) { if (!eq(mul(mul(q, inv(b)), fp_load_const(C_RR())), mul(a, fp_load_const(C_RR())))) atomicAdd(&mismatches[3], 1ull); }
 }
 extern "C" EIP2537_ERROR bls12_b200_selftest(uint64_t* mismatches4, size_t n) {
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return (EIP2537_ERROR)rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
+  Engine& e = *lease.e;
   if ((rc = e.status.reserve(64))) return (EIP2537_ERROR)rc;
   CUDA_TRY2(cudaMemsetAsync(e.status.ptr, 0, 32, e.stream));
   LAUNCH(k_selftest, blocks_for(n, 128), 128, e.stream, n, (unsigned long long*)e.status.ptr);
@@ -990,29 +1564,26 @@ extern "C" EIP2537_ERROR bls12_b200_selftest(uint64_t* mismatches4, size_t n) {
 // lifetime / introspection
 // ------------------------------------------------------------------------------------------
 extern "C" EIP2537_ERROR bls12_b200_init(int device) {
-  Engine* ep;
-  return (EIP2537_ERROR)engine_get(&ep, device);
+  Lease lease;                       // creates the device's first workspace (streams, events, pinned words)
+  return (EIP2537_ERROR)lease.acquire(device);
 }
+// Releases every idle workspace of every device.  Must not race with calls in flight (the caller's contract, as
+// for any library teardown); workspaces leased at this moment are returned to the pool afterwards and stay usable.
 extern "C" void bls12_b200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_init_mu);
+  bls12_b200_comm_destroy();
+  int prev = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); return; }
   for (int d = 0; d < MAX_DEVICES; d++) {
-    Engine& e = g_engines[d];
-    if (!e.ready) continue;
-    std::lock_guard<std::mutex> lk2(e.mu);
-    cudaSetDevice(e.device);
-    cudaStreamSynchronize(e.stream);
-    Buffer* bufs[] = {&e.raw, &e.pts, &e.digits, &e.counts, &e.offsets, &e.block_sums, &e.entries, &e.buckets,
-                      &e.nodes_a, &e.nodes_b, &e.partial, &e.out, &e.status, &e.order, &e.tasks, &e.task_partials, &e.pr_raw, &e.pr_offsets,
-                      &e.pr_lines, &e.pr_tasks, &e.pr_g1, &e.pr_g2, &e.pr_status, &e.pr_f, &e.pr_outs, &e.pr_errs};
-    for (Buffer* b : bufs) b->release();
-    cudaFreeHost(e.h_out);
-    cudaFreeHost(e.h_status);
-    cudaStreamDestroy(e.stream);
-    cudaStreamDestroy(e.stream2);
-    for (int k = 0; k < 8; k++) cudaEventDestroy(e.ev_group[k]);
-    cudaEventDestroy(e.ev_tail);
-    e.ready = false;
+    DevicePool& p = g_pools[d];
+    if (!p.ready.load(std::memory_order_acquire)) continue;
+    std::vector<Engine*> idle;
+    { std::lock_guard<std::mutex> lk2(p.mu); idle.swap(p.idle); p.created -= (int)idle.size(); }
+    cudaSetDevice(p.device);
+    for (Engine* e : idle) { engine_quiesce(e); engine_destroy(e); }
   }
+  cudaSetDevice(prev);
+  g_last_plan.store(nullptr);
 }
 extern "C" const char* bls12_b200_last_error(void) { return g_last_error; }
 extern "C" uint64_t bls12_b200_launch_count(void) { return g_launches.load(); }
@@ -1039,11 +1610,10 @@ extern "C" EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d
 extern "C" EIP2537_ERROR bls12_b200_points_check(int group, const byte* points, size_t n, size_t stride_bytes,
                                                  int check_subgroup, int32_t* codes) {
   if (n == 0) return EIP2537_SUCCESS;
-  Engine* ep;
-  int rc = engine_get(&ep, -1);
+  Lease lease;
+  int rc = lease.acquire(-1);
   if (rc) return (EIP2537_ERROR)rc;
-  Engine& e = *ep;
-  std::lock_guard<std::mutex> lk(e.mu);
+  Engine& e = *lease.e;
   const size_t bytes = n * stride_bytes;
   if ((rc = e.raw.reserve(bytes)) || (rc = e.pr_status.reserve(n * sizeof(int)))) return (EIP2537_ERROR)rc;
   cudaStream_t s = e.stream;

@@ -389,9 +389,13 @@ __global__ void __launch_bounds__(128) k_reduce_inner(const Node<F>* __restrict_
 
 // Horner over the windows from the top down: acc = 2^width[w] * acc + T_w, T_w = roots[w].w.
 // One cooperative lane group walks the ~240 sequential doublings.
+// The result (and, when asked, a copy of the shard's first-error key) may be written through a PEER pointer into
+// another GPU's gather buffer: the multi-GPU exchange is fused into this last kernel of the shard's pipeline.
 template <class F>
-__global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan, XYZZ<F>* __restrict__ acc_io) {
+__global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan, XYZZ<F>* __restrict__ acc_io,
+                                 const unsigned long long* __restrict__ status_src, unsigned long long* __restrict__ status_dst) {
   if (blockIdx.x != 0 || threadIdx.x >= Coop<F>::LANES) return;
+  if (threadIdx.x == 0 && status_dst) *status_dst = *status_src;
   const CoopGroup g = coop_group<F>();
   XYZZ<F> acc = xyzz_inf<F>();
   for (int w = plan.nwin - 1; w >= 0; w--) {
@@ -408,6 +412,30 @@ __global__ void k_finalize(const XYZZ<F>* __restrict__ partials, int count, uint
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   XYZZ<F> acc = partials[0];
   for (int i = 1; i < count; i++) { XYZZ<F> t = partials[i]; xyzz_add(acc, t); }
+  Affine<F> a = xyzz_to_affine(acc);
+  uint32_t w[Wire<F>::POINT_WORDS];
+  encode_point(w, a);
+  for (int i = 0; i < Wire<F>::POINT_WORDS; i++) out_words[i] = w[i];
+}
+
+// One shard's contribution to a multi-GPU MULTIEXP: XYZZ partial sum (192 / 384 B) + first-error key, 512 B
+struct alignas(16) ShardRecord {
+  unsigned char partial[448];
+  unsigned long long status;
+  unsigned long long pad[7];
+};
+// sum the shards' partials unless any shard reported an error (minimum key = first failing pair in input order,
+// eip2537.c:580-592 / :650-668), convert to affine, encode
+template <class F>
+__global__ void k_finalize_records(const ShardRecord* __restrict__ recs, int count, uint32_t* __restrict__ out_words,
+                                   unsigned long long* __restrict__ status_out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned long long st = STATUS_OK;
+  for (int i = 0; i < count; i++) st = recs[i].status < st ? recs[i].status : st;
+  *status_out = st;
+  if (st != STATUS_OK) return;
+  XYZZ<F> acc = *reinterpret_cast<const XYZZ<F>*>(recs[0].partial);
+  for (int i = 1; i < count; i++) { XYZZ<F> t = *reinterpret_cast<const XYZZ<F>*>(recs[i].partial); xyzz_add(acc, t); }
   Affine<F> a = xyzz_to_affine(acc);
   uint32_t w[Wire<F>::POINT_WORDS];
   encode_point(w, a);

@@ -264,28 +264,32 @@ struct Line { Fp2 l0, l1, l4; };             // l0 + l1*w^2 + l4*w^3, already mu
 struct PairingTask { uint32_t first_pair, npairs, slot; };   // slot: index of the chunk's Miller value in fchunk
 
 // Planning state on the device (one instance per batch, zeroed before k_pairing_count):
-//   tasks_for[c]  number of chunks the batch has when cut into chunks of <= c pairs, c = 1..MAX_CHUNK
+//   tasks_for[c]  number of chunks the batch has when cut into chunks of <= c pairs, c = 1..max_chunk
 //   len_count[c][l]  how many of those chunks hold exactly l pairs
 //   chunk  the chunk size k_pairing_plan settles on;  ntasks = tasks_for[chunk];  nslots, cursor[l]: allocation cursors
-constexpr int PAIRING_MAX_CHUNK = 6;
+//   slot_base[k]  (dot engine) tasks are laid out by decreasing length, so the tasks that have a k-th pair are a prefix;
+//                 the k-th pair of task t owns pair slot slot_base[k] + t; npair_slots = pairs of all valid calls
+constexpr int PAIRING_MAX_CHUNK = 16;       // dot-engine kernels (three lanes per chunk); the thread-per-chunk kernel uses <= 6
+constexpr int PAIRING_MAX_CHUNK_THREAD = 6;
 struct PairingPlanState {
   uint32_t tasks_for[PAIRING_MAX_CHUNK + 1];
   uint32_t len_count[PAIRING_MAX_CHUNK + 1][PAIRING_MAX_CHUNK + 1];
   uint32_t cursor[PAIRING_MAX_CHUNK + 1];
-  uint32_t chunk, ntasks, nslots;
+  uint32_t chunk, ntasks, nslots, npair_slots;
+  uint32_t slot_base[PAIRING_MAX_CHUNK + 1];
 };
 
-// Chunk size rule (measured on B200, profiles/r01_bench.md): k_pairing_accumulate holds `wave` threads at once
+// Chunk size rule (measured on B200, profiles/r01_bench.md): the accumulate kernel holds `wave` chunks at once
 // and is latency-bound below that, so the best cut is the one whose task count just fits one wave -- more
-// tasks start a second wave, fewer leave each thread a longer serial chain.  Smallest c with tasks <= wave
-// (MAX_CHUNK when the batch is many waves long: least total work), then larger chunks while the batch still
+// tasks start a second wave, fewer leave each chunk a longer serial chain.  Smallest c with tasks <= wave
+// (max_chunk when the batch is many waves long: least total work), then larger chunks while the batch still
 // fills 85 % of a wave (they share more squarings).
-B200_HD uint32_t pairing_choose_chunk(const uint32_t* tasks_for, uint32_t wave, uint32_t forced) {
-  if (forced >= 1 && forced <= (uint32_t)PAIRING_MAX_CHUNK) return forced;
-  uint32_t c = PAIRING_MAX_CHUNK;
-  for (uint32_t t = 1; t <= (uint32_t)PAIRING_MAX_CHUNK; t++)
+B200_HD uint32_t pairing_choose_chunk(const uint32_t* tasks_for, uint32_t wave, uint32_t forced, uint32_t max_chunk) {
+  if (forced >= 1 && forced <= max_chunk) return forced;
+  uint32_t c = max_chunk;
+  for (uint32_t t = 1; t <= max_chunk; t++)
     if (tasks_for[t] <= wave) { c = t; break; }
-  while (c < (uint32_t)PAIRING_MAX_CHUNK && (uint64_t)tasks_for[c + 1] * 100 >= (uint64_t)wave * 85) c++;
+  while (c < max_chunk && (uint64_t)tasks_for[c + 1] * 100 >= (uint64_t)wave * 85) c++;
   return c;
 }
 
@@ -426,47 +430,78 @@ __global__ void __launch_bounds__(64, 6) k_pairing_lines(const G1Affine* __restr
 }
 
 // one thread per call: decide the call's error code (first failing pair, eip2537.c:1033-1053) and count the
-// chunks it would contribute for every candidate chunk size
+// chunks it would contribute for every candidate chunk size (block-local shared-memory histograms, one global
+// atomic per non-empty counter per block)
 __global__ void __launch_bounds__(128) k_pairing_count(const unsigned long long* __restrict__ offsets, size_t n_calls,
-                                                       const int* __restrict__ status, PairingPlanState* st, int* __restrict__ errs) {
+                                                       const int* __restrict__ status, PairingPlanState* st, int* __restrict__ errs,
+                                                       uint32_t max_chunk) {
+  __shared__ uint32_t h_tasks[PAIRING_MAX_CHUNK + 1];
+  __shared__ uint32_t h_len[PAIRING_MAX_CHUNK + 1][PAIRING_MAX_CHUNK + 1];
+  for (int x = threadIdx.x; x < (PAIRING_MAX_CHUNK + 1) * (PAIRING_MAX_CHUNK + 1); x += blockDim.x) (&h_len[0][0])[x] = 0;
+  if (threadIdx.x <= PAIRING_MAX_CHUNK) h_tasks[threadIdx.x] = 0;
+  __syncthreads();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_calls) return;
-  size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
-  if (first == last) { errs[i] = E_INVALID_LENGTH; return; }
-  for (size_t j = first; j < last; j++)
-    if (status[j] != E_SUCCESS) { errs[i] = status[j]; return; }
-  errs[i] = E_SUCCESS;
-  uint32_t k = (uint32_t)(last - first);
-  for (uint32_t c = 1; c <= (uint32_t)PAIRING_MAX_CHUNK; c++) {
-    uint32_t full = k / c, rem = k % c;
-    atomicAdd(&st->tasks_for[c], full + (rem ? 1 : 0));
-    if (full) atomicAdd(&st->len_count[c][c], full);
-    if (rem) atomicAdd(&st->len_count[c][rem], 1);
+  if (i < n_calls) {
+    size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
+    int code = first == last ? E_INVALID_LENGTH : E_SUCCESS;
+    for (size_t j = first; j < last && code == E_SUCCESS; j++) code = status[j];
+    errs[i] = code;
+    if (code == E_SUCCESS) {
+      uint32_t k = (uint32_t)(last - first);
+      for (uint32_t c = 1; c <= max_chunk; c++) {
+        // ceil(k/c) chunks of BALANCED length (13 pairs at c = 12 are 7 + 6, not 12 + 1): the longest chain bounds a wave
+        uint32_t nch = (k + c - 1) / c, base = k / nch, rem = k % nch;
+        atomicAdd(&h_tasks[c], nch);
+        if (rem) atomicAdd(&h_len[c][base + 1], rem);
+        atomicAdd(&h_len[c][base], nch - rem);
+      }
+    }
   }
+  __syncthreads();
+  for (int x = threadIdx.x; x < (PAIRING_MAX_CHUNK + 1) * (PAIRING_MAX_CHUNK + 1); x += blockDim.x) {
+    uint32_t v = (&h_len[0][0])[x];
+    if (v) atomicAdd(&st->len_count[0][0] + x, v);
+  }
+  if (threadIdx.x <= PAIRING_MAX_CHUNK && h_tasks[threadIdx.x]) atomicAdd(&st->tasks_for[threadIdx.x], h_tasks[threadIdx.x]);
 }
 
 // one thread per call: cut the call into chunks of the chosen size; tasks are laid out by DECREASING length so
-// that the 32 lanes of a warp walk equally long chains (a warp runs as long as its longest lane)
+// that the 32 lanes of a warp walk equally long chains (a warp runs as long as its longest lane).
+// slot_pair (dot engine, may be null): slot_pair[slot_base[k] + t] = index of the k-th pair of task t.
 __global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* __restrict__ offsets, size_t n_calls,
-                                                      const int* __restrict__ errs, uint32_t wave, uint32_t forced_chunk,
+                                                      const int* __restrict__ errs, uint32_t wave, uint32_t forced_chunk, uint32_t max_chunk,
                                                       PairingPlanState* st, PairingTask* __restrict__ tasks,
-                                                      uint32_t* __restrict__ call_first_task) {
+                                                      uint32_t* __restrict__ call_first_task, uint32_t* __restrict__ slot_pair) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_calls) return;
-  const uint32_t chunk = pairing_choose_chunk(st->tasks_for, wave, forced_chunk);
-  if (i == 0) { st->chunk = chunk; st->ntasks = st->tasks_for[chunk]; }
+  const uint32_t chunk = pairing_choose_chunk(st->tasks_for, wave, forced_chunk, max_chunk);
+  uint32_t base_of[PAIRING_MAX_CHUNK + 1], slot_base[PAIRING_MAX_CHUNK + 1];
+  uint32_t run = 0;
+  for (int l = PAIRING_MAX_CHUNK; l >= 1; l--) { base_of[l] = run; run += st->len_count[chunk][l]; }
+  // tasks holding a k-th pair (length > k): the first cnt_k of the length-sorted order
+  uint32_t slots = 0;
+  for (int k = 0; k < PAIRING_MAX_CHUNK; k++) {
+    slot_base[k] = slots;
+    uint32_t cnt = 0;
+    for (int l = k + 1; l <= PAIRING_MAX_CHUNK; l++) cnt += st->len_count[chunk][l];
+    slots += cnt;
+  }
+  if (i == 0) {
+    st->chunk = chunk; st->ntasks = st->tasks_for[chunk]; st->npair_slots = slots;
+    for (int k = 0; k < PAIRING_MAX_CHUNK; k++) st->slot_base[k] = slot_base[k];
+  }
   if (errs[i] != E_SUCCESS) return;
   size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
   uint32_t k = (uint32_t)(last - first), nch = (k + chunk - 1) / chunk;
   uint32_t slot0 = atomicAdd(&st->nslots, nch);
   call_first_task[i] = slot0;
-  uint32_t base_of[PAIRING_MAX_CHUNK + 1];
-  uint32_t run = 0;
-  for (int l = PAIRING_MAX_CHUNK; l >= 1; l--) { base_of[l] = run; run += st->len_count[chunk][l]; }
+  const uint32_t blen = k / nch, rem = k % nch;      // the first `rem` chunks hold blen + 1 pairs (see k_pairing_count)
   for (uint32_t cidx = 0; cidx < nch; cidx++) {
-    uint32_t lo = cidx * chunk, len = k - lo < chunk ? k - lo : chunk;
+    uint32_t lo = cidx * blen + (cidx < rem ? cidx : rem), len = blen + (cidx < rem ? 1 : 0);
     uint32_t pos = base_of[len] + atomicAdd(&st->cursor[len], 1);
     tasks[pos] = PairingTask{(uint32_t)first + lo, len, slot0 + cidx};
+    if (slot_pair)
+      for (uint32_t q = 0; q < len; q++) slot_pair[slot_base[q] + pos] = (uint32_t)first + lo + q;
   }
 }
 

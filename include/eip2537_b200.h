@@ -12,6 +12,17 @@
  * `stream` is a cudaStream_t passed as void* and used as given (NULL = the CUDA default stream);
  * work submitted through these entry points is asynchronous with respect to the host.
  * Every function returns an EIP2537_ERROR; CUDA failures map to EIP2537_MEMORY_ERROR.
+ *
+ * Threading and streams.  Like the reference (src/eip2537.c has no mutable globals) every entry point may be
+ * called from any number of host threads at once.  Each device owns a small pool of WORKSPACES (streams, scratch
+ * buffers in HBM, a pinned staging ring; at most B200_WORKSPACES = 4 per device, created on demand); a call leases
+ * one for its duration, so up to that many host calls per device run concurrently and further callers wait.
+ * The asynchronous device-resident entry points return while their kernels still use the leased workspace: an
+ * event recorded on the caller's stream marks the end of the submission, and whoever leases that workspace next
+ * orders itself after the event (no wait at all for back-to-back submissions on the same stream).  Submissions
+ * from different streams or threads therefore never share scratch memory in flight.
+ * Host input buffers may be pinned or ordinary pageable memory (Go heap slices, Rust Vec); pageable input is
+ * copied through the workspace's pinned ring by a few helper threads (B200_COPY_THREADS, default 4).
  */
 #ifndef __EIP2537_B200_H__
 #define __EIP2537_B200_H__
@@ -25,6 +36,34 @@ extern "C" {
 /* lifetime: lazy init happens on first use; these make it explicit.  device < 0 = current. */
 EIP2537_ERROR bls12_b200_init(int device);
 void bls12_b200_shutdown(void);
+
+/* ---- several GPUs behind the PLAIN ABI (one process).  After bls12_b200_init_multi(ngpu) (ngpu <= 0: all):
+ *   - one bls12_g{1,2}multiexp call of >= 2^17 pairs per GPU is split into contiguous pair ranges, one host
+ *     thread + stream per device, each device pulling its slice over its own PCIe link; the last kernel of every
+ *     shard stores its partial sum and first-error key straight into device 0's gather buffer through NVLink peer
+ *     memory (one exchange step, ngpu x 512 B); device 0 sums, inverts once, encodes.  Same bytes and same codes
+ *     (first failing pair in input order) as the single-GPU call -- replaces the loops of src/eip2537.c:580-606 /
+ *     :650-701 behind the unchanged prototype src/eip2537.h:44-46;
+ *   - bls12_pairing_batch / bls12_g{1,2}multiexp_batch shard by call index, no collective.
+ * bls12_b200_multi_gpus() = the current setting; bls12_b200_device_launch_count(d) = kernels launched on device d. */
+EIP2537_ERROR bls12_b200_init_multi(int ngpu);
+int bls12_b200_multi_gpus(void);
+uint64_t bls12_b200_device_launch_count(int device);
+
+/* ---- one process PER GPU (torchrun / MPI ranks): the C library owns an NCCL communicator (libnccl.so.2 is
+ *      dlopen'ed on first use; single-GPU consumers carry no NCCL dependency).  Rank 0 calls
+ *      bls12_b200_comm_unique_id, the 128 bytes travel to every rank by any means, every rank calls
+ *      bls12_b200_comm_init(world, rank, id) with its device current.  bls12_b200_msm_sharded_* then run this rank's
+ *      shard (pairs index_base .. index_base + n of the global input) and ONE ncclAllGather of world x 512 B
+ *      {partial sum, first-error key}; every rank ends with the same encoded result / code.
+ *      _device: device-resident shard, asynchronous on `stream`, d_status as for bls12_b200_msm_device;
+ *      _host: host-resident shard, synchronous, returns the code, `out` written only on success. */
+EIP2537_ERROR bls12_b200_comm_unique_id(byte* id128);
+EIP2537_ERROR bls12_b200_comm_init(int world, int rank, const byte* id128);
+void bls12_b200_comm_destroy(void);
+EIP2537_ERROR bls12_b200_msm_sharded_device(int group, const void* d_in, size_t n, uint64_t index_base, void* d_out,
+                                            uint64_t* d_status, void* stream);
+EIP2537_ERROR bls12_b200_msm_sharded_host(int group, const byte* in, size_t n, uint64_t index_base, byte* out);
 /* last CUDA error string seen by the engine on this thread ("" if none) */
 const char* bls12_b200_last_error(void);
 /* number of kernels the engine has launched since process start (bench.py's gpu_launches) */
@@ -62,7 +101,10 @@ EIP2537_ERROR bls12_b200_msm_device(int group, const void* d_in, size_t n, void*
 /* size in bytes of one partial sum (XYZZ coordinates, Montgomery limbs) for group 1 / 2 */
 size_t bls12_b200_partial_bytes(int group);
 /* partial sum only (multi-GPU sharding): bls12_b200_partial_bytes(group) bytes at d_partial.
- * index_base is added to pair indices reported in d_status (global index of this shard). */
+ * index_base is added to pair indices reported in d_status (global index of this shard).
+ * PRECONDITION: *d_status must hold ~0 (all ones) before the call, set on the same stream (the kernels only
+ * atomicMin into it so that several shards can share one word); bls12_b200_msm_device and the sharded / host
+ * entry points initialise it themselves.  n must be < 2^31 and n * ceil(256 / window) < 2^32. */
 EIP2537_ERROR bls12_b200_msm_partial_device(int group, const void* d_in, size_t n, uint64_t index_base,
                                             void* d_partial, uint64_t* d_status, void* stream);
 /* same with a HOST-resident shard (pinned or pageable): the shard is streamed in chunks that accumulate
@@ -93,7 +135,7 @@ EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d_points, si
 void bls12_b200_set_checked_msm(int on);
 
 /* PAIRING batches of at most n_calls calls run on the warp-cooperative low-latency kernel (one warp per
- * call), larger ones on the thread-per-chunk throughput kernels.  Default 128 (env B200_PAIRING_COOP_MAX);
+ * call), larger ones on the dot-engine throughput kernels (three lanes per chunk, Fp12 in shared memory).  Default 128 (env B200_PAIRING_COOP_MAX);
  * n_calls < 0 restores the default.  Returns the previous threshold.  Results are identical either way. */
 long bls12_b200_set_pairing_coop_max(long n_calls);
 
@@ -117,6 +159,8 @@ EIP2537_ERROR bls12_b200_last_msm_profile(float* stage_ms4, uint64_t* nonzero_di
 /* same for the pairing batch: stage_ms4 = {decode + subgroup checks, line functions,
  * chunked multi-Miller accumulate, Fp12 product + final exponentiation} */
 EIP2537_ERROR bls12_b200_last_pairing_profile(float* stage_ms4);
+/* pairs per chunk the batch planner chose for the last pairing batch (0 if none) */
+int bls12_b200_last_pairing_chunk(void);
 
 /* ---- on-device self test of the PTX field arithmetic against portable C++ on n pseudo-random
  *      inputs; mismatches4 = {mul, add, sub, inv} mismatch counts (all must be 0) */

@@ -9,6 +9,7 @@ namespace b200 { unsigned long long g_fp_mul_count = 0; }
 #include "../../blst_eip2537_b200/csrc/msm.cuh"
 #include "../../blst_eip2537_b200/csrc/pairing.cuh"
 #include "../../blst_eip2537_b200/csrc/coop12.cuh"
+#include "../../blst_eip2537_b200/csrc/dot12.cuh"
 #include "../../blst_eip2537_b200/csrc/map.cuh"
 
 using namespace b200;
@@ -273,6 +274,39 @@ int emul_coop12_check(const unsigned char* in) {
   fp12_frob(want, f, 2); got = f; coop12_exec_seq<OpFrob<2>>(reinterpret_cast<Fp2*>(&got), nullptr); if (!same(want, got)) bad |= 32;
   return bad;
 }
+// dot12.cuh: term tables, double-width accumulator indexing and separated Montgomery reduction, run sequentially,
+// against the tower functions of pairing.cuh.  Same input as emul_coop12_check; bit mask of mismatches.
+int emul_dot12_check(const unsigned char* in) {
+  Fp12 f, g;
+  Fp* fe = reinterpret_cast<Fp*>(&f);
+  Fp* ge = reinterpret_cast<Fp*>(&g);
+  for (int i = 0; i < 12; i++) {
+    uint32_t w[16];
+    load_words(w, in + 64 * i, 16); if (fp_from_slot(fe[i], w) < 0) return -1;
+    load_words(w, in + 64 * (12 + i), 16); if (fp_from_slot(ge[i], w) < 0) return -1;
+  }
+  auto same = [](const Fp12& a, const Fp12& b) { return memcmp(&a, &b, sizeof(Fp12)) == 0; };
+  int bad = 0;
+  Fp12 want, got;
+  uint32_t fw[144], gw[144], ow[144];
+  dot::fp12_to_words(fw, f);
+  dot::fp12_to_words(gw, g);
+  fp12_sqr(want, f); dot::exec_seq(dot::OP_SQR, ow, fw, nullptr); dot::words_to_fp12(got, ow); if (!same(want, got)) bad |= 1;
+  fp12_mul(want, f, g); dot::exec_seq(dot::OP_MUL, ow, fw, gw); dot::words_to_fp12(got, ow); if (!same(want, got)) bad |= 2;
+  Line ln = {g.c0.c0, g.c0.c1, g.c1.c2};
+  want = f; fp12_mul_by_014(want, ln.l0, ln.l1, ln.l4);
+  dot::exec_seq(dot::OP_MUL014, ow, fw, reinterpret_cast<const uint32_t*>(&ln)); dot::words_to_fp12(got, ow); if (!same(want, got)) bad |= 4;
+  // a single extreme accumulation: 12 products of (p-1)*(p-1) must still reduce correctly
+  {
+    Fp pm1 = fp_load_const(C_P()); pm1.v[0] -= 1;
+    dot::Acc A; dot::acc_zero(A);
+    Fp sum = fp_zero();
+    for (int t = 0; t < 12; t++) { dot::acc_product(A, pm1, pm1); sum = add(sum, mul(pm1, pm1)); }
+    Fp r = dot::acc_reduce(A, 2);
+    if (!eq(r, sum)) bad |= 8;
+  }
+  return bad;
+}
 int emul_g1_in_subgroup(const unsigned char* in128) {
   uint32_t w[32]; load_words(w, in128, 32);
   G1Affine p; int code = decode_point(p, w);
@@ -312,6 +346,6 @@ int emul_map_fp2_to_g2(unsigned char* out256, const unsigned char* in128) {
 }
 // chunk-size rule of the pairing batch planner (pairing.cuh)
 unsigned emul_pairing_choose_chunk(const unsigned* tasks_for7, unsigned wave, unsigned forced) {
-  return pairing_choose_chunk(tasks_for7, wave, forced);
+  return pairing_choose_chunk(tasks_for7, wave, forced, PAIRING_MAX_CHUNK_THREAD);
 }
 }

@@ -204,3 +204,125 @@ def test_multi_gpu_cuda_backend_cross_shard_first_error(product, oracle_c):
     d[160 * 123:160 * 123 + 128] = data[160 * 123:160 * 123 + 128]   # only the later shard fails now
     res = _run_nccl(bytes(d), n, 1, 29544)
     assert [(r[1], r[2]) for r in res] == [(1, None), (1, None)]
+
+
+# ------------------------------------------------------------------------------------------------
+# the plain C ABI driving several GPUs from one process (tests/c/multi_gpu_abi.c)
+# ------------------------------------------------------------------------------------------------
+def test_plain_c_abi_multi_gpu_program():
+    """A plain-C program (no Python, no torch) calls bls12_b200_init_multi + bls12_g{1,2}multiexp: N-GPU bytes equal
+    1-GPU bytes, cross-shard first-error precedence, `out` untouched, every device launched kernels.  With one
+    visible GPU it still runs (N = 1); `gpurun --gpus 2/8` exercises the sharded path."""
+    import json
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "c", "multi_gpu_abi")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "c")], stdout=subprocess.DEVNULL)
+    res = subprocess.run([exe, "19", "0"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["ok"] and line["g1_equal"] and line["g2_equal"] and line["devices_used"] == line["gpus"]
+    assert (line["late_error_code"], line["first_error_code"], line["out_untouched"]) == (1, 3, True)
+
+
+def test_init_multi_python_path_and_pairing_batch_sharding(product, oracle_c):
+    """bls12_b200_init_multi through the ctypes mirror: MULTIEXP of 2^18+ pairs and a 1024-call PAIRING batch give the
+    same bytes with all GPUs as with one (on a one-GPU box both runs are N = 1)."""
+    L = product._native.lib()
+    n = (1 << 18) + 77
+    data, s = wl.g1_msm_input(n, 0x5151)
+    want = oracle_c.g1_gen_mul(s)
+    sys.path.insert(0, ROOT)
+    import bench
+    blob, offs, truth = bench.make_pairing_batch(1024, 0x2537 + 99)
+    try:
+        assert L.bls12_b200_init_multi(1) == 0
+        one = product.G1Multiexp(data)
+        o1, e1 = product.PairingBatch(blob, offs)
+        assert L.bls12_b200_init_multi(0) == 0, L.bls12_b200_last_error()
+        many = product.G1Multiexp(data)
+        o2, e2 = product.PairingBatch(blob, offs)
+    finally:
+        L.bls12_b200_init_multi(1)
+    assert one == want and many == want
+    assert (o1 == o2).all() and (e1 == e2).all() and not e1.any()
+    assert [int(x) for x in o1[:, 31]] == [int(t) for t in truth]
+
+
+# ------------------------------------------------------------------------------------------------
+# concurrency: workspace pool, pageable staging, asynchronous device API on two streams
+# ------------------------------------------------------------------------------------------------
+def test_concurrent_host_threads_scale(product, oracle_c):
+    """8 host threads each running 2^16-pair MULTIEXP calls finish faster than the same calls made serially
+    (the reference is re-entrant; here each call leases its own workspace), and every result is right."""
+    import time
+    n = 1 << 16
+    inputs = [wl.g1_msm_input(n, 0x7000 + t) for t in range(4)]
+    wants = [oracle_c.g1_gen_mul(s) for _, s in inputs]
+    bufs = [np.frombuffer(d, dtype=np.uint8).copy() for d, _ in inputs]      # pageable memory
+    for b_, w in zip(bufs, wants):
+        assert product.G1Multiexp(b_) == w                                     # warm every path
+    reps, nthreads = 4, 8
+    t0 = time.perf_counter()
+    for t in range(nthreads):
+        for _ in range(reps):
+            assert product.G1Multiexp(bufs[t % 4]) == wants[t % 4]
+    serial = time.perf_counter() - t0
+    bad = []
+
+    def work(t):
+        for _ in range(reps):
+            if product.G1Multiexp(bufs[t % 4]) != wants[t % 4]:
+                bad.append(t)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    t0 = time.perf_counter()
+    [x.start() for x in th]
+    [x.join() for x in th]
+    par = time.perf_counter() - t0
+    assert not bad
+    print("serial %.1f ms, 8 threads %.1f ms, speed-up %.2fx" % (serial * 1e3, par * 1e3, serial / par))
+    assert par < serial, (serial, par)
+
+
+def test_pageable_and_pinned_inputs_agree(product, oracle_c):
+    import torch
+    n = (1 << 18) + 1234          # streamed in 6 chunks; the pageable copy goes through the pinned ring
+    data, s = wl.g1_msm_input(n, 0x8181)
+    want = oracle_c.g1_gen_mul(s)
+    pageable = np.frombuffer(data, dtype=np.uint8).copy()
+    pinned = torch.from_numpy(pageable.copy()).pin_memory()
+    assert product.G1Multiexp(pageable) == want
+    assert product.G1Multiexp(pinned) == want
+    bad = bytearray(data)
+    bad[160 * (n - 3) + 127] ^= 1            # error in the last streamed chunk
+    assert product.raw_call_into("bls12_g1multiexp", bytes(bad), 128) == (1, bytes([0xA5]) * 128)
+
+
+def test_device_api_two_streams_stress(product, oracle_c):
+    """Asynchronous device-resident submissions from two CUDA streams (and a host call in between) must not share
+    scratch memory in flight (workspaces were shared and the mutex dropped after enqueue)."""
+    import torch
+    L = product._native.lib()
+    n = 1 << 15
+    ins, wants = [], []
+    for t in range(2):
+        d, s = wl.g1_msm_input(n + 1000 * t, 0x9100 + t)
+        ins.append(torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda())
+        wants.append(oracle_c.g1_gen_mul(s))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(6)] for _ in range(2)]
+    sts = [[torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(6)] for _ in range(2)]
+    small, s_small = wl.g1_msm_input(300, 0x9200)
+    torch.cuda.synchronize()
+    for r in range(6):
+        for t in range(2):
+            rc = L.bls12_b200_msm_device(1, ins[t].data_ptr(), n + 1000 * t, outs[t][r].data_ptr(), sts[t][r].data_ptr(),
+                                         streams[t].cuda_stream)
+            assert rc == 0, L.bls12_b200_last_error()
+        if r % 2 == 0:
+            assert product.G1Multiexp(small) == oracle_c.g1_gen_mul(s_small)      # host call while both streams are busy
+    torch.cuda.synchronize()
+    for t in range(2):
+        for r in range(6):
+            assert bytes(outs[t][r].cpu().numpy()) == wants[t], (t, r)
+            assert int(sts[t][r].item()) == -1
