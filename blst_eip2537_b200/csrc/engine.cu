@@ -1189,10 +1189,12 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   if ((rc = e.pr_g1.reserve(total_pairs * sizeof(G1Affine)))) return rc;
   if ((rc = e.pr_g2.reserve(total_pairs * sizeof(G2Affine)))) return rc;
   if ((rc = e.pr_status.reserve(total_pairs * sizeof(int) + total_pairs + 64))) return rc;
-  if ((rc = e.pr_lines.reserve((size_t)ML_STEPS * total_pairs * sizeof(Line)))) return rc;
+  // dot engine: pair slots are grouped by position inside the chunk, each group padded to a multiple of 32 slots
+  const size_t slot_stride = ((total_pairs + 31) & ~(size_t)31) + 32 * PAIRING_MAX_CHUNK;
+  if ((rc = e.pr_lines.reserve((size_t)ML_STEPS * slot_stride * sizeof(Line)))) return rc;
   if ((rc = e.pr_tasks.reserve(PLAN_BYTES + max_tasks * sizeof(PairingTask) + n_calls * sizeof(uint32_t) + 64))) return rc;
   if ((rc = e.pr_f.reserve(max_tasks * sizeof(Fp12)))) return rc;
-  if ((rc = e.pr_slots.reserve(total_pairs * sizeof(uint32_t) + total_pairs + 64))) return rc;
+  if ((rc = e.pr_slots.reserve(slot_stride * sizeof(uint32_t) + slot_stride + 64))) return rc;
   G1Affine* g1 = (G1Affine*)e.pr_g1.ptr;
   G2Affine* g2 = (G2Affine*)e.pr_g2.ptr;
   int* pstat = (int*)e.pr_status.ptr;
@@ -1203,7 +1205,7 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   uint32_t* call_first = (uint32_t*)(tasks + max_tasks);
   Fp12* f = (Fp12*)e.pr_f.ptr;
   uint32_t* slot_pair = (uint32_t*)e.pr_slots.ptr;
-  unsigned char* skip_slot = (unsigned char*)(slot_pair + total_pairs);
+  unsigned char* skip_slot = (unsigned char*)(slot_pair + slot_stride);
   // Pairs per chunk: chosen on the device from the batch's own shape (pairing_choose_chunk); B200_PAIRING_CHUNK forces it.
   static const int forced_chunk = getenv("B200_PAIRING_CHUNK") ? atoi(getenv("B200_PAIRING_CHUNK")) : 0;
   // B200_PAIRING_ACC=thread selects round 1's thread-per-chunk accumulate (Fp12 in thread-local memory) for A/B runs
@@ -1211,7 +1213,7 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   const uint32_t wave_thread = (uint32_t)e.sm_count * 6 * 64;                     // k_pairing_accumulate: 6 blocks of 64 threads per SM
   static const int dot_blocks = getenv("B200_DOT_BLOCKS") ? atoi(getenv("B200_DOT_BLOCKS")) : DOT_BLOCKS_PER_SM;
   // B200_DOT_WAVE_PCT: the planner's idea of "one wave" as a percentage of the resident chunk slots (developer sweep)
-  static const int wave_pct = getenv("B200_DOT_WAVE_PCT") ? atoi(getenv("B200_DOT_WAVE_PCT")) : 100;
+  static const int wave_pct = getenv("B200_DOT_WAVE_PCT") ? atoi(getenv("B200_DOT_WAVE_PCT")) : 180;
   const uint32_t wave_dot = (uint32_t)((uint64_t)e.sm_count * (dot_blocks == 5 ? 5 : 6) * 32 * wave_pct / 100);   // 32 chunks per block
   const uint32_t fc = (uint32_t)(forced_chunk > 0 ? forced_chunk : 0);
   CUDA_TRY(cudaMemsetAsync(plan_state, 0, sizeof(PairingPlanState), s));
@@ -1243,19 +1245,39 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
     g_pstage.mark(2, s);
     LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs, (uint32_t)PAIRING_MAX_CHUNK_THREAD);
     LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave_thread, fc, (uint32_t)PAIRING_MAX_CHUNK_THREAD,
-           plan_state, tasks, call_first, (uint32_t*)nullptr);
+           (uint32_t)85, plan_state, tasks, call_first, (uint32_t*)nullptr);
     LAUNCH(k_pairing_accumulate, blocks_for(max_tasks, 64), 64, s, tasks, plan_state, lines, skip, total_pairs, f);
     g_pstage.mark(3, s);
     if (small_batch) LAUNCH(k_pairing_call_coop_chunks, (unsigned)n_calls, 32, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
     else             LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
   } else {
+    static const int dot_v = getenv("B200_DOT_V") ? atoi(getenv("B200_DOT_V")) : 3;
+    static const int dot6_blocks = getenv("B200_DOT6_BLOCKS") ? atoi(getenv("B200_DOT6_BLOCKS")) : DOT6_BLOCKS_PER_SM;
+    const uint32_t wave = dot_v == 2 ? wave_dot : (uint32_t)((uint64_t)e.sm_count * (dot6_blocks == 4 ? 4 : 3) * 32 * wave_pct / 100);
+    CUDA_TRY(cudaMemsetAsync(slot_pair, 0xFF, slot_stride * sizeof(uint32_t), s));
     LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs, (uint32_t)PAIRING_MAX_CHUNK);
-    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave_dot, fc, (uint32_t)PAIRING_MAX_CHUNK,
-           plan_state, tasks, call_first, slot_pair);
-    LAUNCH(k_pairing_lines_slots, blocks_for(total_pairs, 64), 64, s, g1, g2, plan_state, slot_pair, total_pairs, (uint32_t*)lines, skip_slot);
+    LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave, fc, (uint32_t)PAIRING_MAX_CHUNK,
+           (uint32_t)97, plan_state, tasks, call_first, slot_pair);
+    LAUNCH(k_pairing_lines_slots, blocks_for(slot_stride, 64), 64, s, g1, g2, plan_state, slot_pair, slot_stride, (uint32_t*)lines, skip_slot);
     g_pstage.mark(2, s);
-    if (dot_blocks == 5) LAUNCH_SMEM(k_pairing_accumulate_dot<5>, blocks_for(max_tasks, 32), 96, DOT_SMEM_BYTES, s, tasks, plan_state, (const uint32_t*)lines, skip_slot, total_pairs, f);
-    else                 LAUNCH_SMEM(k_pairing_accumulate_dot<6>, blocks_for(max_tasks, 32), 96, DOT_SMEM_BYTES, s, tasks, plan_state, (const uint32_t*)lines, skip_slot, total_pairs, f);
+    const unsigned nb = blocks_for(max_tasks, 32);
+    const uint32_t* lt = (const uint32_t*)lines;
+    {  // shared-memory opt-ins (once per device): 54 KB dynamic for the six-role kernel, the largest carve-out for both
+      static std::atomic<unsigned> carved{0};
+      if (!((carved.load() >> e.device) & 1u)) {
+        cudaFuncSetAttribute(k_pairing_accumulate_dot6<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOT6_SMEM_BYTES);
+        cudaFuncSetAttribute(k_pairing_accumulate_dot6<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOT6_SMEM_BYTES);
+        cudaFuncSetAttribute(k_pairing_accumulate_dot6<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_pairing_accumulate_dot<5, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_pairing_accumulate_dot<6, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        (void)cudaGetLastError();
+        carved.fetch_or(1u << e.device);
+      }
+    }
+    if (dot_v != 2 && dot6_blocks == 4) LAUNCH_SMEM(k_pairing_accumulate_dot6<4>, nb, DOT6_THREADS, DOT6_SMEM_BYTES, s, tasks, plan_state, lt, skip_slot, slot_stride, f);
+    else if (dot_v != 2)       LAUNCH_SMEM(k_pairing_accumulate_dot6<3>, nb, DOT6_THREADS, DOT6_SMEM_BYTES, s, tasks, plan_state, lt, skip_slot, slot_stride, f);
+    else if (dot_blocks == 5)  LAUNCH_SMEM((k_pairing_accumulate_dot<5, 1>), nb, 96, DOT_SMEM_BYTES, s, tasks, plan_state, lt, skip_slot, slot_stride, f);
+    else                       LAUNCH_SMEM((k_pairing_accumulate_dot<6, 1>), nb, 96, DOT_SMEM_BYTES, s, tasks, plan_state, lt, skip_slot, slot_stride, f);
     g_pstage.mark(3, s);
     LAUNCH(k_pairing_calls, blocks_for(n_calls, 64), 64, s, n_calls, d_offsets, plan_state, call_first, f, d_outs, d_errs);
   }
@@ -1458,6 +1480,24 @@ __global__ void __launch_bounds__(256) k_imad_carry_probe(int iters, unsigned lo
   if (r == 0x123456789ull || threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
+// dot engine in isolation: per iteration 6 double-width products + ONE reduction (1020 MAC32), operands in registers
+template <class ACC>
+__global__ void __launch_bounds__(256) k_dot_chain(int iters, Fp* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fp x = fp_one(), y = fp_load_const(C_G1GEN());
+  x.v[0] ^= (uint32_t)i;
+  x = fp_reduce_once(x, 0);
+  for (int k = 0; k < iters; k++) {
+    ACC A;
+    dot::acc_zero(A);
+#pragma unroll 1
+    for (int t = 0; t < 6; t++) { dot::acc_product(A, x, y); y.v[0] ^= 1u; }
+    x = dot::acc_reduce(A, 1);
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = x;
+  else if (x.v[0] == 0xdeadbeefu && x.v[5] == 0x12345u) out[blockIdx.x] = x;
+}
+
 extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48) {
   Lease lease;
   int rc = lease.acquire(-1);
@@ -1474,6 +1514,8 @@ extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, in
     if (mode == 0)      LAUNCH(k_fp_chain, nblk, 256, s, iters, (Fp*)e.pts.ptr);
     else if (mode == 1) LAUNCH(k_imad_peak, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
     else if (mode == 2) LAUNCH(k_imad_carry_probe, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
+    else if (mode == 4) LAUNCH(k_dot_chain<dot::Acc>, nblk, 256, s, iters, (Fp*)e.pts.ptr);
+    else if (mode == 5) LAUNCH(k_dot_chain<dot::Acc64>, nblk, 256, s, iters, (Fp*)e.pts.ptr);
     else                LAUNCH(k_imad32_peak, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
     CUDA_TRY2(cudaEventRecord(t1, s));
     CUDA_TRY2(cudaStreamSynchronize(s));

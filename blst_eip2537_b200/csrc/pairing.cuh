@@ -279,17 +279,20 @@ struct PairingPlanState {
   uint32_t slot_base[PAIRING_MAX_CHUNK + 1];
 };
 
-// Chunk size rule (measured on B200, profiles/r01_bench.md): the accumulate kernel holds `wave` chunks at once
-// and is latency-bound below that, so the best cut is the one whose task count just fits one wave -- more
-// tasks start a second wave, fewer leave each chunk a longer serial chain.  Smallest c with tasks <= wave
-// (max_chunk when the batch is many waves long: least total work), then larger chunks while the batch still
-// fills 85 % of a wave (they share more squarings).
-B200_HD uint32_t pairing_choose_chunk(const uint32_t* tasks_for, uint32_t wave, uint32_t forced, uint32_t max_chunk) {
+// Chunk size rule (measured on B200, profiles/r01_bench.md, profiles/r02_pairing.md): the accumulate kernel holds
+// `wave` chunks at once and is latency-bound below that, so the best cut is the one whose task count just fits
+// `wave` -- more tasks start another round, fewer leave each chunk a longer serial chain.  Smallest c with
+// tasks <= wave (max_chunk when the batch is many waves long: least total work), then larger chunks while the
+// batch still fills extend_pct % of it (they share more squarings).  The thread-per-chunk kernel passes its
+// resident thread count and 85; the dot-engine kernel passes 1.8 x its resident chunk slots and 97 (blocks are
+// scheduled longest-first, so ~1.8 rounds of 32-chunk blocks balance the SMs best: chunk 8 at the BASELINE mix).
+B200_HD uint32_t pairing_choose_chunk(const uint32_t* tasks_for, uint32_t wave, uint32_t forced, uint32_t max_chunk,
+                                      uint32_t extend_pct = 85) {
   if (forced >= 1 && forced <= max_chunk) return forced;
   uint32_t c = max_chunk;
   for (uint32_t t = 1; t <= max_chunk; t++)
     if (tasks_for[t] <= wave) { c = t; break; }
-  while (c < max_chunk && (uint64_t)tasks_for[c + 1] * 100 >= (uint64_t)wave * 85) c++;
+  while (c < max_chunk && (uint64_t)tasks_for[c + 1] * 100 >= (uint64_t)wave * extend_pct) c++;
   return c;
 }
 
@@ -470,21 +473,22 @@ __global__ void __launch_bounds__(128) k_pairing_count(const unsigned long long*
 // slot_pair (dot engine, may be null): slot_pair[slot_base[k] + t] = index of the k-th pair of task t.
 __global__ void __launch_bounds__(128) k_pairing_plan(const unsigned long long* __restrict__ offsets, size_t n_calls,
                                                       const int* __restrict__ errs, uint32_t wave, uint32_t forced_chunk, uint32_t max_chunk,
-                                                      PairingPlanState* st, PairingTask* __restrict__ tasks,
+                                                      uint32_t extend_pct, PairingPlanState* st, PairingTask* __restrict__ tasks,
                                                       uint32_t* __restrict__ call_first_task, uint32_t* __restrict__ slot_pair) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_calls) return;
-  const uint32_t chunk = pairing_choose_chunk(st->tasks_for, wave, forced_chunk, max_chunk);
+  const uint32_t chunk = pairing_choose_chunk(st->tasks_for, wave, forced_chunk, max_chunk, extend_pct);
   uint32_t base_of[PAIRING_MAX_CHUNK + 1], slot_base[PAIRING_MAX_CHUNK + 1];
   uint32_t run = 0;
   for (int l = PAIRING_MAX_CHUNK; l >= 1; l--) { base_of[l] = run; run += st->len_count[chunk][l]; }
   // tasks holding a k-th pair (length > k): the first cnt_k of the length-sorted order
+  // (each position's slot range starts at a multiple of 32, so a block's 32 lanes read 128-byte aligned rows)
   uint32_t slots = 0;
   for (int k = 0; k < PAIRING_MAX_CHUNK; k++) {
     slot_base[k] = slots;
     uint32_t cnt = 0;
     for (int l = k + 1; l <= PAIRING_MAX_CHUNK; l++) cnt += st->len_count[chunk][l];
-    slots += cnt;
+    slots += (cnt + 31u) & ~31u;
   }
   if (i == 0) {
     st->chunk = chunk; st->ntasks = st->tasks_for[chunk]; st->npair_slots = slots;

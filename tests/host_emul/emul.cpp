@@ -296,6 +296,8 @@ int emul_dot12_check(const unsigned char* in) {
   Line ln = {g.c0.c0, g.c0.c1, g.c1.c2};
   want = f; fp12_mul_by_014(want, ln.l0, ln.l1, ln.l4);
   dot::exec_seq(dot::OP_MUL014, ow, fw, reinterpret_cast<const uint32_t*>(&ln)); dot::words_to_fp12(got, ow); if (!same(want, got)) bad |= 4;
+  dot::exec_seq(dot::OP_MUL014, ow, fw, reinterpret_cast<const uint32_t*>(&ln), true); dot::words_to_fp12(got, ow); if (!same(want, got)) bad |= 16;
+  fp12_sqr(want, f); dot::exec_seq(dot::OP_SQR, ow, fw, nullptr, true); dot::words_to_fp12(got, ow); if (!same(want, got)) bad |= 32;
   // a single extreme accumulation: 12 products of (p-1)*(p-1) must still reduce correctly
   {
     Fp pm1 = fp_load_const(C_P()); pm1.v[0] -= 1;

@@ -18,8 +18,9 @@ what = sys.argv[1:] or ["micro", "msm", "pairing"]
 
 if "micro" in what:
     nthr = 148 * 2048
-    for mode, name, per in ((1, "imad.wide (operands vary)", 64), (3, "imad lo+hi pairs", 64), (2, "imad.wide carry chains", 24), (0, "fp_mul", 1)):
-        iters = 2000 if mode == 1 else 1000
+    for mode, name, per in ((1, "imad.wide (operands vary)", 64), (3, "imad lo+hi pairs", 64), (2, "imad.wide carry chains", 24), (0, "fp_mul", 1),
+                            (4, "dot6 engine, 32-bit accumulator words (MAC32)", 1020), (5, "dot6 engine, 64-bit accumulator pairs (MAC32)", 1020)):
+        iters = 2000 if mode == 1 else (300 if mode >= 4 else 1000)
         L.bls12_b200_fp_microbench(mode, nthr, iters, ctypes.byref(ms), None)
         ops = nthr * iters * per
         print("%s: %.3f ms, %.3e ops/s" % (name, ms.value, ops / (ms.value * 1e-3)), flush=True)
