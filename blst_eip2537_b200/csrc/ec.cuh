@@ -114,6 +114,35 @@ B200_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q) {
   acc.zzz = mul(acc.zzz, ppp);
 }
 
+#ifdef __CUDACC__
+// the same mixed addition over Fp with the multiplication loop unrolled ROWS rows per iteration (fp.cuh mul_unrolled:
+// fewer register moves on the multiply pipe; measured in profiles/r02_k1_probes.md)
+template <int ROWS>
+__device__ __forceinline__ void xyzz_madd_unrolled(XYZZ<Fp>& acc, const Affine<Fp>& q) {
+#ifdef __CUDA_ARCH__
+  if (is_inf(q)) return;
+  if (is_inf(acc)) { acc = xyzz_from_affine(q); return; }
+  Fp u2 = mul_unrolled<ROWS>(q.x, acc.zz);
+  Fp s2 = mul_unrolled<ROWS>(q.y, acc.zzz);
+  Fp p = sub(u2, acc.x);
+  Fp r = sub(s2, acc.y);
+  if (is_zero(p)) {
+    if (is_zero(r)) acc = xyzz_dbl_affine(q);
+    else            acc = xyzz_inf<Fp>();
+    return;
+  }
+  Fp pp = mul_unrolled<ROWS>(p, p);
+  Fp ppp = mul_unrolled<ROWS>(p, pp);
+  Fp qq = mul_unrolled<ROWS>(acc.x, pp);
+  Fp x3 = sub(sub(mul_unrolled<ROWS>(r, r), ppp), dbl(qq));
+  acc.y = mul_diff(r, sub(qq, x3), acc.y, ppp);
+  acc.x = x3;
+  acc.zz = mul_unrolled<ROWS>(acc.zz, pp);
+  acc.zzz = mul_unrolled<ROWS>(acc.zzz, ppp);
+#endif
+}
+#endif
+
 // acc += q (both XYZZ)   (add-2008-s)
 template <class F>
 B200_HD_NI void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {

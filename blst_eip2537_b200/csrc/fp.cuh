@@ -325,6 +325,87 @@ B200_D Fp mul(const Fp& a, const Fp& b_in) {
   for (int i = 0; i < 12; i++) r.v[i] = x[i];
   return fp_reduce_once(r, x[12]);
 }
+// ---- experimental variants of `mul` (bls12_b200_fp_microbench modes 6..8; profiles/r02_k1_probes.md) -----------------
+// The rolled loop above shifts the 12 multiplier limbs down by two after every iteration: 60 register moves per
+// multiplication, which ptxas emits as IMAD.MOV.U32 -- and those occupy the SAME multiply pipe as the 300 wide products.
+// Variant A: three iterations of four rows (shift by four: 16 moves).  Variant B: two iterations of six rows (6 moves).
+// Variant C: the multiplier limbs are parked in shared memory and fetched by index (LSU pipe, no moves).
+// register move that ptxas must leave on the ALU pipe (a byte permute with the identity selector), for the shifts
+B200_D uint32_t alu_move(uint32_t v) {
+  uint32_t r;
+  asm volatile("prmt.b32 %0, %1, 0, 0x3210;" : "=r"(r) : "r"(v));
+  return r;
+}
+template <int ROWS_PER_ITER, bool ALU_SHIFT = false>
+B200_D Fp mul_unrolled(const Fp& a, const Fp& b_in) {
+  using namespace detail;
+  static_assert(ROWS_PER_ITER == 2 || ROWS_PER_ITER == 4 || ROWS_PER_ITER == 6 || ROWS_PER_ITER == 12, "rows per iteration");
+  uint32_t x[13], y[13], b[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { b[i] = b_in.v[i]; x[i] = 0; }
+  x[12] = 0;
+#pragma unroll 1
+  for (int it = 0; it < 12 / ROWS_PER_ITER; it++) {
+#pragma unroll
+    for (int r = 0; r < ROWS_PER_ITER; r += 2) {
+      uint32_t m;
+      mad_row(x, a.v, b[r]);
+      mul_row(y, a.v + 1, b[r]); y[12] = 0;
+      m = x[0] * B200_M0;
+      B200_MADP_ROW(x, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+      B200_MADP_ROW(y, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+      fold(y, x);
+      mad_row(y, a.v, b[r + 1]);
+      mul_row(x, a.v + 1, b[r + 1]); x[12] = 0;
+      m = y[0] * B200_M0;
+      B200_MADP_ROW(y, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+      B200_MADP_ROW(x, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+      fold(x, y);
+    }
+    if (ROWS_PER_ITER < 12) {
+#pragma unroll
+      for (int i = 0; i < 12 - ROWS_PER_ITER; i++) b[i] = ALU_SHIFT ? alu_move(b[i + ROWS_PER_ITER]) : b[i + ROWS_PER_ITER];
+    }
+  }
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = x[i];
+  return fp_reduce_once(r, x[12]);
+}
+#ifdef __CUDACC__
+// multiplier limbs in shared memory: slot = 12 words, word i of thread t at slot[i * stride]
+B200_D Fp mul_bsmem(const Fp& a, const Fp& b_in, uint32_t* slot, int stride) {
+  using namespace detail;
+  uint32_t x[13], y[13];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { slot[i * stride] = b_in.v[i]; x[i] = 0; }
+  x[12] = 0;
+  uint32_t b0 = slot[0], b1 = slot[stride];
+#pragma unroll 1
+  for (int it = 0; it < 6; it++) {
+    uint32_t m;
+    const uint32_t n0 = slot[((2 * it + 2) % 12) * stride], n1 = slot[((2 * it + 3) % 12) * stride];   // next pair, in flight
+    mad_row(x, a.v, b0);
+    mul_row(y, a.v + 1, b0); y[12] = 0;
+    m = x[0] * B200_M0;
+    B200_MADP_ROW(x, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+    B200_MADP_ROW(y, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+    fold(y, x);
+    mad_row(y, a.v, b1);
+    mul_row(x, a.v + 1, b1); x[12] = 0;
+    m = y[0] * B200_M0;
+    B200_MADP_ROW(y, m, B200_P0, B200_P2, B200_P4, B200_P6, B200_P8, B200_P10);
+    B200_MADP_ROW(x, m, B200_P1, B200_P3, B200_P5, B200_P7, B200_P9, B200_P11);
+    fold(x, y);
+    b0 = n0; b1 = n1;
+  }
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = x[i];
+  return fp_reduce_once(r, x[12]);
+}
+#endif
+
 // a*b - c*d with ONE Montgomery reduction: the rows of both products are accumulated before each reduction
 // row, so the pair costs 2*144 + 156 multiply-accumulates instead of 2*300.  The point formulas end in such a
 // difference (Y3 = R*(Q - X3) - Y1*PPP).  c is negated first, so the accumulator holds a*b + (p-c)*d; it stays

@@ -283,19 +283,20 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
   return r;
 }
 
-template <class F>
+template <class F, int ROWS = 2>
 __device__ __forceinline__ void accumulate_segment(XYZZ<F>& acc, const Affine<F>* __restrict__ pts,
                                                    const uint32_t* __restrict__ entries, uint32_t start, uint32_t cnt) {
   for (uint32_t k = 0; k < cnt; k++) {
     uint32_t e = __ldg(entries + start + k);
     Affine<F> pt = load_affine(pts + (e & 0x7fffffffu));
     if (e >> 31) pt.y = neg(pt.y);
-    xyzz_madd(acc, pt);
+    if constexpr (ROWS != 2 && sizeof(F) == sizeof(Fp)) xyzz_madd_unrolled<ROWS>(acc, pt);
+    else xyzz_madd(acc, pt);
   }
 }
 
 // one thread per bucket, buckets taken in order of decreasing size; at most `cap` entries each
-template <class F>
+template <class F, int ROWS = 2>
 __global__ void __launch_bounds__(128, 4) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                     const uint32_t* __restrict__ order, uint32_t nbuckets_total, uint32_t cap,
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const Affine<F>* __restri
   if (add_to_existing && cnt == 0) return;   // streamed chunks: the bucket keeps what earlier chunks left
   XYZZ<F> acc;
   if (add_to_existing) acc = buckets[b]; else acc = xyzz_inf<F>();
-  accumulate_segment(acc, pts, entries, offsets[b], cnt < cap ? cnt : cap);
+  accumulate_segment<F, ROWS>(acc, pts, entries, offsets[b], cnt < cap ? cnt : cap);
   buckets[b] = acc;
 }
 // one thread per overflow task

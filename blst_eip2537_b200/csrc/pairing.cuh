@@ -330,6 +330,9 @@ __global__ void k_codes_to_status(const int* __restrict__ codes, size_t n, size_
 
 // one thread per pair: decode + subgroup checks in the reference's order
 // (G1 decode, G1 subgroup, G2 decode, G2 subgroup; eip2537.c:1036-1053); status[j] = first failing code
+// CHECK_G2 = false: the G2 membership test is left to k_pairing_lines_slots, whose Miller-loop walk T = [|z|]Q IS the
+// 64-bit ladder of that test (the dot-engine pipeline; saves ~1,170 of the 2,256 Fp-mul per pair of this stage).
+template <bool CHECK_G2>
 __global__ void __launch_bounds__(64, 6) k_pairing_decode(const uint32_t* __restrict__ raw, size_t total_pairs,
                                                        G1Affine* __restrict__ g1, G2Affine* __restrict__ g2, int* __restrict__ status) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,10 +350,34 @@ __global__ void __launch_bounds__(64, 6) k_pairing_decode(const uint32_t* __rest
 #pragma unroll
     for (int k = 0; k < 16; k++) { uint4 v = __ldg(src + 8 + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
     code = decode_point(q, w);
-    if (code == E_SUCCESS && !g2_in_subgroup(q)) code = E_NOT_IN_SUBGROUP;
+    if (CHECK_G2 && code == E_SUCCESS && !g2_in_subgroup(q)) code = E_NOT_IN_SUBGROUP;
   }
   status[j] = code;
   if (code == E_SUCCESS) { g1[j] = p; g2[j] = q; }
+}
+
+// Deferred G2 membership (dot-engine pipeline), two small per-call passes that keep the reference's precedence
+// "first failing pair in input order, G1 checks before G2 checks inside a pair" (eip2537.c:1033-1053):
+//  k_pairing_early_fix  a call that already failed (errs != 0 from k_pairing_count) may hold an EARLIER pair whose only
+//                       fault is G2 membership: run the exact ladder on the pairs before the failing one (rare path)
+//  k_pairing_late_errs  after the line kernel has written the deferred G2 results into status[]: first failing pair
+__global__ void __launch_bounds__(64) k_pairing_early_fix(const unsigned long long* __restrict__ offsets, size_t n_calls,
+                                                          const G2Affine* __restrict__ g2, int* __restrict__ status, int* __restrict__ errs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_calls || errs[i] == E_SUCCESS || errs[i] == E_INVALID_LENGTH) return;
+  size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
+  for (size_t j = first; j < last && status[j] == E_SUCCESS; j++) {
+    G2Affine q = g2[j];
+    if (!g2_in_subgroup(q)) { status[j] = E_NOT_IN_SUBGROUP; errs[i] = E_NOT_IN_SUBGROUP; return; }
+  }
+}
+__global__ void __launch_bounds__(128) k_pairing_late_errs(const unsigned long long* __restrict__ offsets, size_t n_calls,
+                                                           const int* __restrict__ status, int* __restrict__ errs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_calls || errs[i] != E_SUCCESS) return;
+  size_t first = (size_t)(offsets[i] / 384), last = (size_t)(offsets[i + 1] / 384);
+  for (size_t j = first; j < last; j++)
+    if (status[j] != E_SUCCESS) { errs[i] = status[j]; return; }
 }
 
 // Latency variant for small batches: 32 pairs per block of two warps, warp 0 takes the G1 member of each pair, warp 1

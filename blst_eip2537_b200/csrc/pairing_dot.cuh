@@ -1,36 +1,43 @@
 // pairing_dot.cuh -- K5 throughput kernels built on the dot-product Fp12 engine (dot12.cuh).
 //
-//   k_pairing_lines_slots     one thread per PAIR SLOT: the 68 line functions of a pair, evaluated at P, written
-//                             word-transposed (lines_t[(step*72 + word) * stride + slot]) so that the accumulate
-//                             kernel's warps read them fully coalesced.  Slots follow the task order of the batch
-//                             plan (k-th pairs of consecutive tasks are consecutive slots).
-//   k_pairing_accumulate_dot  32 chunks per block of three warps; the Fp12 accumulators live in shared memory
-//                             (two buffers, word-transposed: conflict-free), role r = warp index computes the
-//                             coefficients of w^r and w^(r+3) of every operation, one barrier per operation.
+//   k_pairing_lines_slots      one thread per PAIR SLOT: the 68 line functions of a pair, evaluated at P, written
+//                              word-transposed (lines_t[(step*72 + word) * stride + slot]) so that the accumulate
+//                              kernel reads them as 128-byte rows.  Slots follow the task order of the batch plan
+//                              (k-th pairs of consecutive tasks are consecutive slots).  The walk T = [|z|]Q of the
+//                              Miller loop doubles as the ladder of the G2 membership test (deferred from decode).
+//   k_pairing_accumulate_dot6  32 chunks per block of SIX warps, warp r owns the coefficient of w^r of every chunk;
+//                              Fp12 accumulators in shared memory (two buffers, word-transposed: conflict-free), the
+//                              line of the next sparse product staged by cp.async, one barrier per operation.
+//   k_pairing_final_dot6       same geometry, 32 CALLS per block: product of the chunk values, final exponentiation
+//                              as an interpreted program, is-one.
 //
-// Replaces blst_miller_loop + blst_fp12_mul of /root/reference/src/eip2537.c:1060-1065 for all pairs of a chunk at
-// once (shared squarings; only the boolean of the call is observable).
+// Replaces blst_miller_loop + blst_fp12_mul + blst_final_exp + blst_fp12_is_one of
+// /root/reference/src/eip2537.c:1060-1078 for all pairs of a chunk / all calls of a batch at once (shared squarings;
+// only the boolean of the call is observable).
 #pragma once
 #include "dot12.cuh"
 
 namespace b200 {
 #ifdef __CUDACC__
 
-// blocks of 96 threads per SM: 5 (<= 136 registers) or 6 (<= 112 registers; 6 x 37 KB is all the shared memory there is)
-static constexpr int DOT_BLOCKS_PER_SM = 6;
-static constexpr int DOT_SMEM_BYTES = 2 * 144 * 32 * 4;
 static constexpr int LINE_WORDS = 72;           // Line = 3 Fp2 = 6 Fp = 72 words
 
 __global__ void __launch_bounds__(64, 6) k_pairing_lines_slots(const G1Affine* __restrict__ g1, const G2Affine* __restrict__ g2,
                                                             const PairingPlanState* __restrict__ st, const uint32_t* __restrict__ slot_pair,
-                                                            size_t stride, uint32_t* __restrict__ lines_t, unsigned char* __restrict__ skip_slot) {
+                                                            size_t stride, uint32_t* __restrict__ lines_t, unsigned char* __restrict__ skip_slot,
+                                                            int* __restrict__ status) {
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= st->npair_slots) return;
   const size_t j = slot_pair[q];
   if (j == 0xFFFFFFFFu) { skip_slot[q] = 1; return; }           // padding slot (slot bases are multiples of 32)
   G1Affine p = g1[j];
   G2Affine qq = g2[j];
-  if (is_inf(p) || is_inf(qq)) { skip_slot[q] = 1; return; }   // contributes 1
+  if (is_inf(qq)) { skip_slot[q] = 1; return; }                  // infinity is a member; the pair contributes 1 (Appendix D-2)
+  if (is_inf(p)) {                                               // contributes 1, but Q must still be in G2 (eip2537.c:1051)
+    skip_slot[q] = 1;
+    if (!g2_in_subgroup(qq)) status[j] = E_NOT_IN_SUBGROUP;
+    return;
+  }
   skip_slot[q] = 0;
   G2Proj t;
   t.x = qq.x; t.y = qq.y; t.z = fp2_one();
@@ -47,75 +54,19 @@ __global__ void __launch_bounds__(64, 6) k_pairing_lines_slots(const G1Affine* _
       for (int x = 0; x < LINE_WORDS; x++) dst[(size_t)x * stride] = w[x];
     }
   }
-}
-
-// f buffers (dynamic shared memory, dot::dot_smem): word (c, limb) of lane L at buf*4608 + (c*12 + limb)*32 + L,
-// c = 2*k + {0 re, 1 im}, k = power of w
-template <int BLOCKS, int PAIR64>
-__global__ void __launch_bounds__(96, BLOCKS) k_pairing_accumulate_dot(
-    const PairingTask* __restrict__ tasks, const PairingPlanState* __restrict__ st, const uint32_t* __restrict__ lines_t,
-    const unsigned char* __restrict__ skip_slot, size_t stride, Fp12* __restrict__ fchunk) {
-  using dot::dot_smem;
-  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-  const uint32_t ntasks = st->ntasks;
-  if (blockIdx.x * 32u >= ntasks) return;
-  const uint32_t t = blockIdx.x * 32u + lane;
-  const bool live = t < ntasks;
-  PairingTask task = PairingTask{0, 0, 0};
-  if (live) task = tasks[t];
-  const uint32_t npairs = live ? task.npairs : 0;
-  uint32_t kmax = npairs;
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, kmax, o); kmax = v > kmax ? v : kmax; }
-  // f = 1
-  for (int q = 0; q < 2; q++) {
-    const int k = role + 3 * q;
-    for (int comp = 0; comp < 2; comp++)
-      for (int l = 0; l < 12; l++) dot_smem[((2 * k + comp) * 12 + l) * 32 + lane] = (k == 0 && comp == 0) ? C_ONE()[l] : 0u;
+  // Deferred G2 membership test psi(Q) == [z]Q (blst_p2_affine_in_g2, eip2537.c:1051): the walk above ended at
+  // T = [|z|]Q in homogeneous coordinates, and z < 0, so the test is psi(Q) == -T.  The step formulas are incomplete;
+  // every exceptional event (T = infinity, T = +-Q at an addition step -- possible only for points of small order
+  // outside G2) forces Z = 0 from then on, in which case the exact ladder decides.
+  bool member;
+  if (is_zero(t.z)) {
+    member = g2_in_subgroup(qq);
+  } else {
+    const Fp2 px = mulo(conj(qq.x), fp2_load_const(C_PSI_CX()));
+    const Fp2 py = mulo(conj(qq.y), fp2_load_const(C_PSI_CY()));
+    member = eq(mulo(px, t.z), t.x) && eq(mulo(py, t.z), neg(t.y));
   }
-  __syncthreads();
-  uint32_t cur = 0;      // word offset of the current buffer: 0 or 4608
-  auto run_op = [&](int op, const dot::GlobalWords& G, bool keep) {
-    const dot::SmemWords F{cur + (uint32_t)lane};
-    uint32_t* dst = dot_smem + (cur ^ 4608u) + lane;     // 4608 = 0x1200: xor toggles between 0 and 4608
-#pragma unroll 1
-    for (int q = 0; q < 4; q++) {
-      const int c = 2 * (role + 3 * (q >> 1)) + (q & 1);
-      Fp r;
-      if (keep) r = dot::dot_eval_dev<BLOCKS + 10 * PAIR64>(dot::op_row(op, c), dot::op_count(op, c), F, G);
-      else      r = F.load(c);
-#pragma unroll
-      for (int l = 0; l < 12; l++) dst[(c * 12 + l) * 32] = r.v[l];
-    }
-    __syncthreads();
-    cur ^= 4608u;
-  };
-  int s = 0;
-#pragma unroll 1
-  for (int i = 62; i >= 0; i--) {
-    run_op(dot::OP_SQR, dot::GlobalWords{lines_t, 0}, true);
-    const int nsteps = ((B200_Z_ABS >> i) & 1) ? 2 : 1;
-    for (int a = 0; a < nsteps; a++, s++) {
-      for (uint32_t k = 0; k < kmax; k++) {
-        bool active = k < npairs;
-        size_t slot = 0;
-        if (active) { slot = (size_t)st->slot_base[k] + t; active = skip_slot[slot] == 0; }
-        run_op(dot::OP_MUL014, dot::GlobalWords{lines_t + (size_t)s * LINE_WORDS * stride + slot, (uint32_t)stride}, active);
-      }
-    }
-  }
-  // conj (the loop ran over |z|, z < 0): negate the odd powers of w; back to the memory order of Fp12
-  if (live) {
-    const dot::SmemWords F{cur + (uint32_t)lane};
-    Fp2* out = reinterpret_cast<Fp2*>(&fchunk[task.slot]);
-    for (int q = 0; q < 2; q++) {
-      const int k = role + 3 * q;
-      Fp2 v;
-      v.c0 = F.load(2 * k); v.c1 = F.load(2 * k + 1);
-      if (k & 1) v = neg(v);
-      out[dot::mem_of_wpow(k)] = v;
-    }
-  }
+  if (!member) status[j] = E_NOT_IN_SUBGROUP;
 }
 
 // ---- six roles per chunk, lines staged in shared memory by cp.async -------------------------------------------
@@ -218,6 +169,129 @@ __global__ void __maxnreg__(BLOCKS == 3 ? 112 : 80) k_pairing_accumulate_dot6(
     if (role & 1) v = neg(v);
     out[dot::mem_of_wpow(role)] = v;
   }
+}
+
+// ---- final exponentiation on the dot engine ---------------------------------------------------------------------
+// Replaces blst_final_exp + blst_fp12_is_one (/root/reference/src/eip2537.c:1070-1078) for 32 calls per block of six
+// role warps (same geometry as the accumulate kernel).  Round 1 ran this stage one THREAD per call: 16384 threads,
+// a 12.9 ms chain of ~7,700 dependent multiplications.  Here the chain is walked operation by operation with the
+// six coefficients of each Fp12 value computed side by side; three Fp12 buffers live in shared memory, values that
+// are needed again much later (f, f^((z-1)^2 (z+p))) are parked in HBM.
+// The exponent chain is a small PROGRAM (generated once on the host, engine.cu final_exp_program) interpreted by
+// every block, so the dot engine is inlined at exactly one site.
+enum FinalOp : uint32_t { FX_MUL = 0, FX_CYC = 1, FX_CONJ = 2, FX_FROB1 = 3, FX_FROB2 = 4, FX_COPY = 5, FX_PARK = 6, FX_UNPARK = 7, FX_INV = 8 };
+static constexpr int FX_PARK_SLOTS = 2;
+__host__ __device__ inline uint32_t fx_encode(uint32_t op, uint32_t d, uint32_t x, uint32_t y) { return op | (d << 8) | (x << 12) | (y << 16); }
+
+__global__ void __maxnreg__(112) k_pairing_final_dot6(size_t n_calls, const unsigned long long* __restrict__ offsets,
+                                                      const PairingPlanState* __restrict__ st, const uint32_t* __restrict__ call_first_task,
+                                                      const Fp12* __restrict__ fchunk, const uint32_t* __restrict__ prog, int prog_len,
+                                                      Fp12* __restrict__ park, uint32_t* __restrict__ outs, const int* __restrict__ errs) {
+  using dot::dot_smem;
+  __shared__ int not_one[32];
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const size_t call = (size_t)blockIdx.x * 32 + lane;
+  const bool in_range = call < n_calls;
+  const bool live = in_range && errs[call] == E_SUCCESS;
+  if (role == 0 && in_range) {
+    uint32_t* out = outs + 8 * call;
+    for (int k = 0; k < 8; k++) out[k] = 0;
+  }
+  if (role == 0) not_one[lane] = 0;
+  const uint32_t chunk = st->chunk;
+  uint32_t nch = 0, base = 0;
+  if (live) {
+    const uint32_t npairs = (uint32_t)(offsets[call + 1] / 384 - offsets[call] / 384);
+    nch = (npairs + chunk - 1) / chunk;
+    base = call_first_task[call];
+  }
+  uint32_t nchmax = nch;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, nchmax, o); nchmax = v > nchmax ? v : nchmax; }
+  if (nchmax == 0) return;           // no valid call in this block (block-uniform)
+  const int mem_idx = dot::mem_of_wpow(role);
+  auto words = [&](uint32_t b) { return dot::SmemWords{b * (uint32_t)DOT6_F_WORDS + (uint32_t)lane}; };
+  auto ld_coef = [&](uint32_t b) { Fp2 v; v.c0 = words(b).load(2 * role); v.c1 = words(b).load(2 * role + 1); return v; };
+  auto st_coef = [&](uint32_t b, const Fp2& v) {
+    uint32_t* dst = dot_smem + b * DOT6_F_WORDS + lane;
+#pragma unroll
+    for (int l = 0; l < 12; l++) { dst[((2 * role) * 12 + l) * 32] = v.c0.v[l]; dst[((2 * role + 1) * 12 + l) * 32] = v.c1.v[l]; }
+  };
+  auto load_chunk = [&](uint32_t b, uint32_t idx) {       // chunk value idx of this lane's call (1 beyond its last chunk)
+    Fp2 v = role == 0 ? fp2_one() : fp2_zero();
+    if (idx < nch) v = reinterpret_cast<const Fp2*>(&fchunk[base + idx])[mem_idx];
+    st_coef(b, v);
+  };
+  load_chunk(0, 0);
+  __syncthreads();
+  // steps: (nchmax - 1) x {load chunk j -> buffer 1, product -> the other of buffers 0 / 2}, a copy back to buffer 0 if
+  // the product ended in buffer 2, then the exponent program
+  const int pre = 2 * ((int)nchmax - 1);
+  const int fix = (nchmax > 1 && ((nchmax - 1) & 1)) ? 1 : 0;
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int step = 0; step < pre + fix + prog_len; step++) {
+    uint32_t ins;
+    if (step < pre) {
+      if ((step & 1) == 0) { load_chunk(1, (uint32_t)(step / 2 + 1)); __syncthreads(); continue; }
+      ins = fx_encode(FX_MUL, acc ^ 2u, acc, 1);
+      acc ^= 2u;
+    } else if (step < pre + fix) {
+      ins = fx_encode(FX_COPY, 0, 2, 0);
+    } else {
+      ins = prog[step - pre - fix];
+    }
+    const uint32_t opc = ins & 0xffu, d = (ins >> 8) & 15u, x = (ins >> 12) & 15u, y = (ins >> 16) & 15u;
+    if (opc <= FX_CYC) {
+      const dot::SmemWords F = words(x), G = words(y);
+      const int op = opc == FX_MUL ? dot::OP_MUL : dot::OP_CYC;
+      uint32_t* dst = dot_smem + d * DOT6_F_WORDS + lane;
+#pragma unroll 1
+      for (int q = 0; q < 2; q++) {
+        const int c = 2 * role + q;
+        Fp r = dot::dot_eval_smem(dot::op_row(op, c), dot::op_count(op, c), F, G);
+        if (opc == FX_CYC) r = dot::cyc_epilogue(r, F.load(c), (role & 1) != 0);
+#pragma unroll
+        for (int l = 0; l < 12; l++) dst[(c * 12 + l) * 32] = r.v[l];
+      }
+    } else if (opc == FX_CONJ) {
+      if (role & 1) st_coef(x, neg(ld_coef(x)));
+    } else if (opc == FX_FROB1 || opc == FX_FROB2) {
+      Fp2 v = ld_coef(x);
+      if (opc == FX_FROB1) v = conj(v);
+      st_coef(x, mulo(v, fp2_load_const((opc == FX_FROB1 ? C_FROB1() : C_FROB2()) + 24 * role)));
+    } else if (opc == FX_COPY) {
+      st_coef(d, ld_coef(x));
+    } else if (opc == FX_PARK) {
+      if (live) reinterpret_cast<Fp2*>(&park[(size_t)y * n_calls + call])[mem_idx] = ld_coef(x);
+    } else if (opc == FX_UNPARK) {
+      Fp2 v = role == 0 ? fp2_one() : fp2_zero();
+      if (live) v = reinterpret_cast<const Fp2*>(&park[(size_t)y * n_calls + call])[mem_idx];
+      st_coef(d, v);
+    } else if (opc == FX_INV) {
+      if (role == 0) {         // one lane per call runs the tower inversion (one Fp inversion inside)
+        Fp12 v, vi;
+        Fp2* m = reinterpret_cast<Fp2*>(&v);
+        for (int k = 0; k < 6; k++) { m[dot::mem_of_wpow(k)].c0 = words(x).load(2 * k); m[dot::mem_of_wpow(k)].c1 = words(x).load(2 * k + 1); }
+        fp12_inv(vi, v);
+        const Fp2* mi = reinterpret_cast<const Fp2*>(&vi);
+        uint32_t* dst = dot_smem + d * DOT6_F_WORDS + lane;
+        for (int k = 0; k < 6; k++) {
+          const Fp2& cf = mi[dot::mem_of_wpow(k)];
+          for (int l = 0; l < 12; l++) { dst[((2 * k) * 12 + l) * 32] = cf.c0.v[l]; dst[((2 * k + 1) * 12 + l) * 32] = cf.c1.v[l]; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // is-one: the program leaves the result in buffer 0
+  {
+    const Fp2 v = ld_coef(0);
+    const bool ok = role == 0 ? eq(v, fp2_one()) : is_zero(v);
+    if (!ok) atomicOr(&not_one[lane], 1);
+  }
+  __syncthreads();
+  if (role == 0 && live && not_one[lane] == 0) outs[8 * call + 7] = 0x01000000u;   // byte 31 of the 32-byte big-endian word
 }
 
 #endif  // __CUDACC__

@@ -137,6 +137,60 @@ def test_pairing_batch_baseline_shape_per_call_vs_oracle(product, oracle_c):
     assert all(int(outs[j][31]) == int(truth[j]) for j in untouched)
 
 
+def _g2_small_order_points():
+    """Points of E'(Fp2) of small order (13 and 23 divide the cofactor of G2): the incomplete Miller-loop step
+    formulas hit their exceptional cases on these, which is what the deferred G2 membership test must survive."""
+    h2 = 0x5d543a95414e7f1091d50792876a202cd91de4547085abaa68a205b2e5a7ddfa628f1cb4d9e82ef21537e293a6691ae1616ec6e786f0c70cf1c38e31c7238e5
+    n = h2 * po.R
+    base = po.decode_g2(_g2_outside_subgroup())[1]
+    pts = []
+    for ell in (13, 23):      # the ell-parts of E'(Fp2) are (Z/ell)^2: exponent ell, order ell^2
+        assert n % (ell * ell) == 0
+        pt = po.ec_mul(po.F2_OPS, n // (ell * ell), base)
+        if pt is not None:
+            assert po.ec_mul(po.F2_OPS, ell, pt) is None
+            pts.append(po.encode_g2(pt))
+    return pts
+
+
+def test_deferred_g2_membership_keeps_codes_and_precedence(product, oracle_c):
+    """Large batches decide G2 membership inside the line kernel (its walk of [|z|]Q is the ladder of the test).
+    Every call is compared with the oracle: G2 faults before / after G1 faults, infinite G1 with a bad Q, points of
+    small order (exceptional chain -> exact ladder), and ordinary true / false calls around them."""
+    q_out = _g2_outside_subgroup()
+    small = _g2_small_order_points()
+    assert small, "no small-order point constructed"
+    order3 = po.encode_g1((0, 2))
+    off1 = G1B[:64] + po.fp_to_bytes(5)
+    rng = wl.SplitMix64(0x2537 + 61)
+    good = lambda k, truth=True: wl.pairing_call(k, rng, truth)
+    special = [
+        G1B + q_out + off1 + G2B,                       # G2 fault at pair 0 precedes the G1 fault at pair 1 -> 2
+        off1 + G2B + G1B + q_out,                       # the G1 fault comes first -> 1
+        G1B + G2B + bytes(128) + q_out,                 # infinite G1, Q outside G2 -> 2 (Q is still checked)
+        G1B + G2B + G1B + bytes(256),                   # infinite G2 is a member -> fine
+        order3 + q_out,                                 # G1 membership is checked before G2 -> 2 either way
+        good(3)[:384 * 2] + G1B + q_out,                # fault in the last pair
+    ]
+    for sp in small:
+        special += [G1B + sp, G1B + G2B + G1B + sp + G1B + G2B, bytes(128) + sp]
+    calls = []
+    for j in range(200):                                # > 128 calls: the dot-engine pipeline
+        calls.append(special[j // 7 % len(special)] if j % 7 == 3 else good(2 + j % 9, j % 4 != 1))
+    blob = b"".join(calls)
+    offs = [0]
+    for c in calls:
+        offs.append(offs[-1] + len(c))
+    outs, errs = product.PairingBatch(blob, offs)
+    seen = set()
+    for j, c in enumerate(calls):
+        code, ref = oracle_c.call("pairing", c)
+        assert int(errs[j]) == code, (j, int(errs[j]), code)
+        assert bytes(outs[j]) == (ref if code == 0 else bytes(32)), j
+        seen.add(code)
+    assert seen == {0, 1, 2}
+
+
 # ------------------------------------------------------------------------------------------------
 # multi-GPU: the real CUDA backend under torch.multiprocessing + NCCL
 # ------------------------------------------------------------------------------------------------

@@ -82,6 +82,25 @@ def table_mul():
     return out
 
 
+def table_cyc():
+    """Bilinear part Q_k of the Granger-Scott cyclotomic squaring (pairing.cuh fp12_cyclotomic_sqr) in powers of w:
+         Q_0 = a_0^2 + xi a_3^2   Q_3 = 2 a_0 a_3      Q_2 = a_1^2 + xi a_4^2   Q_5 = 2 a_1 a_4
+         Q_4 = a_2^2 + xi a_5^2   Q_1 = 2 xi a_2 a_5
+    the new coefficient is a_k' = 3 Q_k - 2 a_k (k even) or 3 Q_k + 2 a_k (k odd): the linear epilogue is done by the caller."""
+    out = [[] for _ in range(12)]
+
+    def put(k, terms):
+        out[2 * k] += terms[0]
+        out[2 * k + 1] += terms[1]
+    for k, (i, j) in ((0, (0, 3)), (2, (1, 4)), (4, (2, 5))):
+        put(k, square_terms(i, False))
+        put(k, square_terms(j, True))
+    put(3, product_terms(0, 0, 0, 3, False, 2))
+    put(5, product_terms(0, 1, 0, 4, False, 2))
+    put(1, product_terms(0, 2, 0, 5, True, 2))
+    return out
+
+
 def emit(name, tab, width):
     lines = ["__device__ __constant__ static const uint16_t D12_%s_DEV[12][%d] = {" % (name, width)]
     host = ["static const uint16_t D12_%s_HOST[12][%d] = {" % (name, width)]
@@ -104,11 +123,12 @@ def main():
     parts.append(emit("SQR", table_sqr(), 8))
     parts.append(emit("MUL014", table_mul014(), 6))
     parts.append(emit("MUL", table_mul(), 12))
+    parts.append(emit("CYC", table_cyc(), 4))
     parts.append("} }  // namespace b200::dot")
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "blst_eip2537_b200", "csrc", "dot12_tables.cuh")
     with open(out, "w") as fh:
         fh.write("\n".join(parts) + "\n")
-    for nm, t in (("sqr", table_sqr()), ("mul014", table_mul014()), ("mul", table_mul())):
+    for nm, t in (("sqr", table_sqr()), ("mul014", table_mul014()), ("mul", table_mul()), ("cyc", table_cyc())):
         print(nm, [len(r) for r in t], "products", sum(len(r) for r in t))
 
 

@@ -19,7 +19,10 @@ what = sys.argv[1:] or ["micro", "msm", "pairing"]
 if "micro" in what:
     nthr = 148 * 2048
     for mode, name, per in ((1, "imad.wide (operands vary)", 64), (3, "imad lo+hi pairs", 64), (2, "imad.wide carry chains", 24), (0, "fp_mul", 1),
-                            (4, "dot6 engine, 32-bit accumulator words (MAC32)", 1020), (5, "dot6 engine, 64-bit accumulator pairs (MAC32)", 1020)):
+                            (4, "dot6 engine, 32-bit accumulator words (MAC32)", 1020), (5, "dot6 engine, 64-bit accumulator pairs (MAC32)", 1020),
+                            (6, "fp_mul, per-thread multiplier, 2 rows/iter (product)", 1), (7, "fp_mul, 4 rows/iter", 1), (8, "fp_mul, 6 rows/iter", 1),
+                            (9, "fp_mul, fully unrolled", 1), (10, "fp_mul, multiplier limbs from shared memory", 1),
+                            (11, "fp_mul, 2 rows/iter, ALU-pipe shifts", 1), (12, "fp_mul, 6 rows/iter, ALU-pipe shifts", 1)):
         iters = 2000 if mode == 1 else (300 if mode >= 4 else 1000)
         L.bls12_b200_fp_microbench(mode, nthr, iters, ctypes.byref(ms), None)
         ops = nthr * iters * per
