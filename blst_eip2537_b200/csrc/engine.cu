@@ -347,6 +347,7 @@ static unsigned long long g_last_entries = 0;
 template <class F>
 struct MsmRun {
   MsmPlan plan;
+  bool glv;
   size_t nbt, chunk_cap;
   Affine<F>* pts; int* digits; uint32_t *counts, *cursors, *offsets, *block_sums, *entries, *order, *bin_total, *bin_start;
   OrderCounters* oc; OverflowTask* tasks; BigBucket* big; XYZZ<F>* task_partials; XYZZ<F>* buckets;
@@ -355,7 +356,10 @@ struct MsmRun {
 
 template <class F>
 static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
-  r.plan = make_plan(choose_window(n_total, sizeof(F) == sizeof(Fp2)));
+  // checked MULTIEXP: subgroup-proven inputs allow the GLV split (msm.cuh glv_split): 2n points, 128-bit scalars
+  r.glv = g_checked_msm.load() != 0 && !(getenv("B200_NO_GLV") && atoi(getenv("B200_NO_GLV")));
+  if (r.glv) { n_total *= 2; chunk_n *= 2; }
+  r.plan = make_plan(choose_window(n_total, sizeof(F) == sizeof(Fp2)), r.glv ? 128 : 256);
   const MsmPlan& plan = r.plan;
   r.nbt = (size_t)plan.nwin * plan.nb;   // total buckets, uniform layout
   r.chunk_cap = chunk_n;
@@ -403,34 +407,44 @@ static int msm_feed(Engine& e, MsmRun<F>& r, const uint32_t* d_raw, size_t n, ui
   const size_t nbt = r.nbt;
   if (first) g_stage.mark(0, s);
   CUDA_TRY(cudaMemsetAsync(r.counts, 0, 2 * nbt * sizeof(uint32_t), s));
-  LAUNCH(k_decode<F>, blocks_for(n, 128), 128, s, d_raw, n, r.pts, d_status, (size_t)index_base);
+  const int glv = r.glv ? 1 : 0;
+  const size_t nv = r.glv ? 2 * n : n;      // virtual points fed to the bucket machinery
+  LAUNCH(k_decode<F>, blocks_for(n, 128), 128, s, d_raw, n, r.pts, d_status, (size_t)index_base, glv);
   if (g_checked_msm.load()) {   // opt-in "checked MSM" (SURVEY.md 8(f)-4): reject points outside G1/G2 with code 2
     int rc2 = e.pr_status.reserve(n * sizeof(int));
     if (rc2) return rc2;
     LAUNCH(k_points_check<F>, blocks_for(n, 64), 64, s, d_raw, n, Wire<F>::PAIR_WORDS, 1, (int*)e.pr_status.ptr);
     LAUNCH(k_codes_to_status, blocks_for(n, 256), 256, s, (const int*)e.pr_status.ptr, n, (size_t)index_base, d_status);
   }
-  LAUNCH(k_digits<F>, blocks_for(n, 256), 256, s, d_raw, n, r.pts, plan, r.digits, r.counts);
+  LAUNCH(k_digits<F>, blocks_for(n, 256), 256, s, d_raw, n, r.pts, plan, r.digits, r.counts, glv);
   unsigned nblk = blocks_for(nbt, 1024);
   LAUNCH(k_scan_blocks, nblk, 1024, s, r.counts, r.offsets, r.block_sums, (uint32_t)nbt);
   LAUNCH(k_scan_sums, 1, 1024, s, r.block_sums, nblk);
   LAUNCH(k_scan_fix, nblk, 1024, s, r.offsets, r.block_sums, (uint32_t)nbt);
-  LAUNCH(k_scatter, blocks_for(n * plan.nwin, 256), 256, s, r.digits, n, plan, r.offsets, r.cursors, r.entries);
+  LAUNCH(k_scatter, blocks_for(nv * plan.nwin, 256), 256, s, r.digits, nv, plan, r.offsets, r.cursors, r.entries);
   // size-ordered bucket schedule + overflow plan for oversized buckets
-  const size_t total_digits = n * plan.nwin;
+  const size_t total_digits = nv * plan.nwin;
   uint32_t cap = (uint32_t)(4 * (total_digits / nbt + 1) + 64);
   CUDA_TRY(cudaMemsetAsync(r.bin_total, 0, 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters), s));
   LAUNCH(k_order_hist, nblk, 1024, s, r.counts, r.offsets, (uint32_t)nbt, cap, r.bin_total, r.oc, r.big, r.tasks);
   LAUNCH(k_order_scan, 1, 1024, s, r.bin_total, r.bin_start);
   LAUNCH(k_order_scatter, nblk, 1024, s, r.counts, (uint32_t)nbt, r.bin_start, r.order);
   if (first) g_stage.mark(1, s);
-  static const int acc_rows = getenv("B200_ACC_ROWS") ? atoi(getenv("B200_ACC_ROWS")) : 2;   // developer switch: multiply-loop unrolling in k_accumulate<Fp>
-  if (sizeof(F) == sizeof(Fp) && acc_rows == 6)
-    LAUNCH((k_accumulate<F, 6>), blocks_for(nbt, 128), 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, first ? 0 : 1, r.buckets);
-  else if (sizeof(F) == sizeof(Fp) && acc_rows == 12)
-    LAUNCH((k_accumulate<F, 12>), blocks_for(nbt, 128), 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, first ? 0 : 1, r.buckets);
-  else
-    LAUNCH((k_accumulate<F, 2>), blocks_for(nbt, 128), 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, first ? 0 : 1, r.buckets);
+  // multiply-loop unrolling in k_accumulate<Fp> (6 rows per iteration: -2.3 % on the kernel, profiles/r02_k1_probes.md) and the
+  // register budget of k_accumulate<Fp2>; B200_ACC_ROWS / B200_ACC_G2_BLOCKS are developer switches
+  static const int acc_rows = getenv("B200_ACC_ROWS") ? atoi(getenv("B200_ACC_ROWS")) : 6;
+  static const int g2_blocks = getenv("B200_ACC_G2_BLOCKS") ? atoi(getenv("B200_ACC_G2_BLOCKS")) : 4;
+  const unsigned acc_grid = blocks_for(nbt, 128);
+  const int add_flag = first ? 0 : 1;
+  if (sizeof(F) == sizeof(Fp)) {
+    if (acc_rows == 6)       LAUNCH((k_accumulate<F, 6, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+    else if (acc_rows == 12) LAUNCH((k_accumulate<F, 12, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+    else                     LAUNCH((k_accumulate<F, 2, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+  } else {
+    if (g2_blocks == 2)      LAUNCH((k_accumulate<F, 2, 2>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+    else if (g2_blocks == 3) LAUNCH((k_accumulate<F, 2, 3>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+    else                     LAUNCH((k_accumulate<F, 2, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+  }
   const size_t tasks_bound = total_digits / cap + 2;
   LAUNCH(k_accumulate_overflow<F>, blocks_for(tasks_bound, 128), 128, s, r.pts, r.entries, r.tasks, r.oc, r.task_partials);
   LAUNCH(k_merge_overflow<F>, blocks_for(tasks_bound * 32, 128), 128, s, r.big, r.oc, r.task_partials, r.buckets);
@@ -508,6 +522,8 @@ static int msm_pipeline(Engine& e, const uint32_t* d_raw, size_t n, uint64_t ind
 // Go passes heap slices (go/blst_eip2537.go:74), Rust passes Vec / stack arrays: ordinary pageable memory, which
 // cudaMemcpyAsync moves at ~7 GB/s through the driver's own bounce buffer.  Here a small pool of host threads
 // copies the caller's bytes into the workspace's pinned ring while earlier ring slots are in flight over PCIe.
+static std::atomic<int> g_ngpu{1};      // bls12_b200_init_multi: devices a single large call is sharded over
+
 struct CopyPool {
   struct Job { unsigned char* d; const unsigned char* s; size_t n; std::atomic<int>* left; };
   std::vector<std::thread> th;
@@ -519,7 +535,8 @@ struct CopyPool {
   void start() {
     std::lock_guard<std::mutex> lk(mu);
     if (nthreads) return;
-    int want = getenv("B200_COPY_THREADS") ? atoi(getenv("B200_COPY_THREADS")) : 4;
+    // B200_COPY_THREADS per device in use (default 4), never more than half the host's hardware threads
+    int want = (getenv("B200_COPY_THREADS") ? atoi(getenv("B200_COPY_THREADS")) : 4) * (g_ngpu.load() > 1 ? g_ngpu.load() : 1);
     int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && want > hw / 2) want = hw / 2;
     if (want < 1) want = 1;
@@ -543,13 +560,14 @@ struct CopyPool {
   // dst <- src with every pool thread and the caller taking a share
   void copy(unsigned char* d, const unsigned char* s, size_t n) {
     start();
-    const int parts = nthreads + 1;
+    const int share = nthreads < 4 ? nthreads : 4;      // one copy never takes more than 4 helpers: concurrent callers share the pool
+    const int parts = share + 1;
     const size_t per = ((n / parts) + 4095) & ~(size_t)4095;
     std::atomic<int> left{0};
     size_t off = 0;
     {
       std::lock_guard<std::mutex> lk(mu);
-      for (int i = 0; i < nthreads && off + per < n; i++, off += per) { left.fetch_add(1); q.push_back(Job{d + off, s + off, per, &left}); }
+      for (int i = 0; i < share && off + per < n; i++, off += per) { left.fetch_add(1); q.push_back(Job{d + off, s + off, per, &left}); }
     }
     cv.notify_all();
     memcpy(d + off, s + off, n - off);
@@ -676,7 +694,6 @@ static int msm_finish_host(Engine& e, const ShardRecord* recs, int count, unsign
 // single-GPU pipeline; its LAST kernel (k_window_combine) stores the partial sum and the first-error key straight
 // into device 0's gather buffer through NVLink peer memory (the one exchange step: G x 512 B), and device 0 sums,
 // inverts once and encodes.  Error precedence is the minimum (global pair index << 8 | code) over the shards.
-static std::atomic<int> g_ngpu{1};
 static bool g_peer_ok[MAX_DEVICES] = {};
 static constexpr size_t MULTI_MIN_PAIRS_PER_GPU = (size_t)1 << 17;
 
@@ -1748,21 +1765,43 @@ extern "C" EIP2537_ERROR bls12_b200_points_check_device(int group, const void* d
   CUDA_TRY2(cudaGetLastError());
   return EIP2537_SUCCESS;
 }
+static int points_check_on_device(int device, int group, const byte* points, size_t n, size_t stride_bytes, int check_subgroup, int32_t* codes) {
+  Lease lease;
+  int rc = lease.acquire(device);
+  if (rc) return rc;
+  Engine& e = *lease.e;
+  const size_t bytes = n * stride_bytes;
+  if ((rc = e.raw.reserve(bytes)) || (rc = e.pr_status.reserve(n * sizeof(int)))) return rc;
+  cudaStream_t s = e.stream;
+  if ((rc = h2d_copy(e, (unsigned char*)e.raw.ptr, points, bytes, host_pointer_is_pageable(points), s))) return rc;
+  EIP2537_ERROR r = bls12_b200_points_check_device(group, e.raw.ptr, n, stride_bytes, check_subgroup, (int32_t*)e.pr_status.ptr, (void*)s);
+  if (r) return r;
+  CUDA_TRY(cudaMemcpyAsync(codes, e.pr_status.ptr, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return E_SUCCESS;
+}
+// independent per point: after bls12_b200_init_multi(G) a large array is cut into G contiguous ranges, one host thread
+// and device each (SURVEY.md 8(e) "batched decode / subgroup checks": no exchange at all, the codes land in place)
 extern "C" EIP2537_ERROR bls12_b200_points_check(int group, const byte* points, size_t n, size_t stride_bytes,
                                                  int check_subgroup, int32_t* codes) {
   if (n == 0) return EIP2537_SUCCESS;
-  Lease lease;
-  int rc = lease.acquire(-1);
-  if (rc) return (EIP2537_ERROR)rc;
-  Engine& e = *lease.e;
-  const size_t bytes = n * stride_bytes;
-  if ((rc = e.raw.reserve(bytes)) || (rc = e.pr_status.reserve(n * sizeof(int)))) return (EIP2537_ERROR)rc;
-  cudaStream_t s = e.stream;
-  CUDA_TRY2(cudaMemcpyAsync(e.raw.ptr, points, bytes, cudaMemcpyHostToDevice, s));
-  EIP2537_ERROR r = bls12_b200_points_check_device(group, e.raw.ptr, n, stride_bytes, check_subgroup, (int32_t*)e.pr_status.ptr, (void*)s);
-  if (r) return r;
-  CUDA_TRY2(cudaMemcpyAsync(codes, e.pr_status.ptr, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY2(cudaStreamSynchronize(s));
+  if (stride_bytes & 15) { snprintf(g_last_error, sizeof g_last_error, "stride must be a multiple of 16"); return EIP2537_MEMORY_ERROR; }
+  int G = g_ngpu.load();
+  if ((size_t)G > n / 4096) G = (int)(n / 4096);
+  if (G <= 1) return (EIP2537_ERROR)points_check_on_device(-1, group, points, n, stride_bytes, check_subgroup, codes);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> msgs(G);
+  auto work = [&](int d) {
+    const size_t lo = n * (size_t)d / G, hi = n * (size_t)(d + 1) / G;
+    rcs[d] = points_check_on_device(d, group, points + lo * stride_bytes, hi - lo, stride_bytes, check_subgroup, codes + lo);
+    if (rcs[d]) msgs[d] = g_last_error;
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < G; d++) th.emplace_back(work, d);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < G; d++)
+    if (rcs[d]) { snprintf(g_last_error, sizeof g_last_error, "device %d: %s", d, msgs[d].c_str()); return (EIP2537_ERROR)rcs[d]; }
   return EIP2537_SUCCESS;
 }
 // stage_ms4 = {decode + subgroup checks, line functions, chunked accumulate, product + final exp}

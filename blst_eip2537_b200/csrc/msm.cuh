@@ -24,7 +24,7 @@
 
 namespace b200 {
 
-// Window layout.  The 256 scalar bits are cut into nwin = ceil(256/c) windows whose widths are c or
+// Window layout.  The scalar bits (256; 128 on the checked GLV path) are cut into nwin = ceil(bits/c) windows whose widths are c or
 // c-1 bits (so every c is usable, not only the divisors of 256).  All windows but the top one use
 // signed digits (|d| <= 2^(width-1)); the top window is unsigned and absorbs the last carry, so there
 // is no 257th-bit window.  When 256 is not a multiple of c the top window is one of the narrow ones
@@ -38,18 +38,18 @@ struct MsmPlan {
   uint16_t bitpos[128];  // first bit of window w
 };
 
-static inline MsmPlan make_plan(int c) {
+static inline MsmPlan make_plan(int c, int nbits = 256) {
   MsmPlan p;
   p.c = c;
-  p.nwin = (256 + c - 1) / c;
-  const int narrow = p.nwin * c - 256;           // windows that are c-1 bits wide (top window first)
+  p.nwin = (nbits + c - 1) / c;
+  const int narrow = p.nwin * c - nbits;         // windows that are c-1 bits wide (top window first)
   int pos = 0;
   for (int w = 0; w < p.nwin; w++) {
     // narrow windows: the top one, then every other slot from the top down as needed
     bool is_narrow = (p.nwin - 1 - w) < narrow;
     p.width[w] = (uint8_t)(is_narrow ? c - 1 : c);
   }
-  // (widths are assigned so that the narrow windows sit at the top; their sum is exactly 256)
+  // (widths are assigned so that the narrow windows sit at the top; their sum is exactly nbits)
   for (int w = 0; w < p.nwin; w++) { p.bitpos[w] = (uint16_t)pos; pos += p.width[w]; }
   const int top_w = p.width[p.nwin - 1];
   p.log_nb = (c - 1 > top_w) ? c - 1 : top_w;
@@ -63,9 +63,77 @@ static constexpr unsigned long long STATUS_OK = ~0ull;
 
 // ------------------------------------------------------------------------------------------ decode
 // status key = (pair index << 8) | code ; atomicMin keeps the first failing pair
+// Checked MULTIEXP (opt-in): every point is PROVEN to lie in the r-torsion subgroup, so the fast path
+// the reference left as a TODO (eip2537.c:340, :401) becomes legal: scalars are reduced mod r and split as
+// k = q*z^2 + t (t, q < 2^128), and k*P = t*P + q*E(P) with the cheap endomorphism E = [z^2]:
+//   G1: phi(P) = (beta x, y) = [-z^2]P  =>  E(P) = (beta x, -y);   G2: psi(Q) = [z]Q  =>  E(Q) = psi^2(Q) = (N(cx) x, N(cy) y)
+// The pipeline then sees 2n points with 128-bit scalars: the same bucket additions, HALF the windows (half the tail).
+__device__ __forceinline__ Affine<Fp> glv_image(const Affine<Fp>& p) {
+  Affine<Fp> r;
+  r.x = mul(p.x, fp_load_const(C_BETA()));
+  r.y = neg(p.y);
+  return r;
+}
+__device__ __forceinline__ Affine<Fp2> glv_image(const Affine<Fp2>& p) {
+  const Fp2 cx = fp2_load_const(C_PSI_CX()), cy = fp2_load_const(C_PSI_CY());
+  const Fp nx = add(sqr(cx.c0), sqr(cx.c1)), ny = add(sqr(cy.c0), sqr(cy.c1));      // psi^2 multiplies by the norms
+  Affine<Fp2> r;
+  r.x = mul_fp(p.x, nx);
+  r.y = mul_fp(p.y, ny);
+  return r;
+}
+// k (8 little-endian words, any 256-bit value) -> k mod r -> (t, q) with k mod r = q*z^2 + t, 4 words each
+__device__ __forceinline__ void glv_split(const uint32_t* k_in, uint32_t* t4, uint32_t* q4) {
+  const uint32_t R[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+  const uint32_t Z2[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};
+  const uint32_t MU[5] = {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u};   // floor(2^256 / z^2)
+  uint32_t k[8];
+  for (int i = 0; i < 8; i++) k[i] = k_in[i];
+  for (int rep = 0; rep < 2; rep++) {          // 2^256 < 3r: at most two subtractions
+    uint32_t d[8];
+    uint64_t bw = 0;
+    for (int i = 0; i < 8; i++) { uint64_t x = (uint64_t)k[i] - R[i] - bw; d[i] = (uint32_t)x; bw = (x >> 32) & 1; }
+    if (!bw) for (int i = 0; i < 8; i++) k[i] = d[i];
+  }
+  // q = floor(k * MU / 2^256) (never above the true quotient, at most 1 below): words 8..11 of the 13-word product
+  uint32_t prod[13];
+  for (int i = 0; i < 13; i++) prod[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 5; j++) { uint64_t x = (uint64_t)k[i] * MU[j] + prod[i + j] + c; prod[i + j] = (uint32_t)x; c = x >> 32; }
+    prod[i + 5] = (uint32_t)c;
+  }
+  uint32_t q[4] = {prod[8], prod[9], prod[10], prod[11]};
+  // t = k - q*z^2 (fits in 5 words before the correction)
+  uint32_t qz[8];
+  for (int i = 0; i < 8; i++) qz[i] = 0;
+  for (int i = 0; i < 4; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 4; j++) { uint64_t x = (uint64_t)q[i] * Z2[j] + qz[i + j] + c; qz[i + j] = (uint32_t)x; c = x >> 32; }
+    qz[i + 4] = (uint32_t)c;
+  }
+  uint32_t t[5];
+  {
+    uint64_t bw = 0;
+    for (int i = 0; i < 5; i++) { uint64_t x = (uint64_t)k[i] - qz[i] - bw; t[i] = (uint32_t)x; bw = (x >> 32) & 1; }
+  }
+  for (int rep = 0; rep < 2; rep++) {          // t >= z^2: one more z^2 fits
+    uint32_t d[5];
+    uint64_t bw = 0;
+    for (int i = 0; i < 5; i++) { uint64_t x = (uint64_t)t[i] - (i < 4 ? Z2[i] : 0u) - bw; d[i] = (uint32_t)x; bw = (x >> 32) & 1; }
+    if (!bw) {
+      for (int i = 0; i < 5; i++) t[i] = d[i];
+      uint64_t c = 1;
+      for (int i = 0; i < 4; i++) { uint64_t x = (uint64_t)q[i] + c; q[i] = (uint32_t)x; c = x >> 32; }
+    }
+  }
+  for (int i = 0; i < 4; i++) { t4[i] = t[i]; q4[i] = q[i]; }
+}
+
+// glv != 0: also writes the endomorphism image E(P_i) at pts[n + i]
 template <class F>
 __global__ void __launch_bounds__(128) k_decode(const uint32_t* __restrict__ raw, size_t n, Affine<F>* __restrict__ pts,
-                                                unsigned long long* status, size_t index_base) {
+                                                unsigned long long* status, size_t index_base, int glv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   constexpr int PW = Wire<F>::POINT_WORDS, SW = Wire<F>::PAIR_WORDS;
@@ -80,6 +148,7 @@ __global__ void __launch_bounds__(128) k_decode(const uint32_t* __restrict__ raw
   int code = decode_point(pt, w);
   if (code != E_SUCCESS) atomicMin(status, ((unsigned long long)(index_base + i) << 8) | (unsigned)code);
   pts[i] = pt;
+  if (glv) pts[n + i] = is_inf(pt) ? pt : glv_image(pt);
 }
 
 // ------------------------------------------------------------------------------------------ digits
@@ -90,10 +159,11 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* k, int bit, int 
   return v & ((1u << c) - 1);
 }
 
-// digits[w*n + i] = signed digit of scalar i in window w (0 = skip); counts[w*nb + |d|-1]++
+// digits[w*nv + v] = signed digit of virtual point v in window w (0 = skip); counts[w*nb + |d|-1]++.
+// Plain path: nv = n, one 256-bit scalar per pair.  glv: nv = 2n, pair i feeds t to point i and q to point n + i.
 template <class F>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ raw, size_t n, const Affine<F>* __restrict__ pts,
-                                                MsmPlan plan, int* __restrict__ digits, uint32_t* counts) {
+                                                MsmPlan plan, int* __restrict__ digits, uint32_t* counts, int glv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   constexpr int PW = Wire<F>::POINT_WORDS, SW = Wire<F>::PAIR_WORDS;
@@ -105,23 +175,33 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ raw
   const uint32_t* pw = reinterpret_cast<const uint32_t*>(pts + i);
   uint32_t any = 0;
   for (int t = 0; t < (int)(sizeof(Affine<F>) / 4); t++) any |= pw[t];
-  bool inf = (any == 0);
-  uint32_t carry = 0;
-  for (int w = 0; w < plan.nwin; w++) {
-    int d;
-    const int wd = plan.width[w];
-    uint32_t raw_d = window_bits(k, plan.bitpos[w], wd) + carry;
-    if (w < plan.nwin - 1) {
-      if (raw_d > (1u << (wd - 1))) { d = (int)raw_d - (int)(1u << wd); carry = 1; }
-      else                          { d = (int)raw_d; carry = 0; }
-    } else {
-      d = (int)raw_d;   // top window: unsigned, <= 2^width
-    }
-    if (inf) d = 0;
-    digits[(size_t)w * n + i] = d;
-    if (d != 0) {
-      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      atomicAdd(&counts[(size_t)w * plan.nb + (mag - 1)], 1u);
+  const bool inf = (any == 0);
+  const size_t nv = glv ? 2 * n : n;
+  uint32_t half[2][8];
+  if (glv) {
+    for (int t = 0; t < 8; t++) { half[0][t] = 0; half[1][t] = 0; }
+    glv_split(k, half[0], half[1]);
+  }
+  for (int part = 0; part < (glv ? 2 : 1); part++) {
+    const uint32_t* kk = glv ? half[part] : k;
+    const size_t v = i + (size_t)part * n;
+    uint32_t carry = 0;
+    for (int w = 0; w < plan.nwin; w++) {
+      int d;
+      const int wd = plan.width[w];
+      uint32_t raw_d = window_bits(kk, plan.bitpos[w], wd) + carry;
+      if (w < plan.nwin - 1) {
+        if (raw_d > (1u << (wd - 1))) { d = (int)raw_d - (int)(1u << wd); carry = 1; }
+        else                          { d = (int)raw_d; carry = 0; }
+      } else {
+        d = (int)raw_d;   // top window: unsigned, <= 2^width
+      }
+      if (inf) d = 0;
+      digits[(size_t)w * nv + v] = d;     // (|d| reaches 2^16 in an unsigned 16-bit top window: 17 bits with the sign)
+      if (d != 0) {
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        atomicAdd(&counts[(size_t)w * plan.nb + (mag - 1)], 1u);
+      }
     }
   }
 }
@@ -296,8 +376,9 @@ __device__ __forceinline__ void accumulate_segment(XYZZ<F>& acc, const Affine<F>
 }
 
 // one thread per bucket, buckets taken in order of decreasing size; at most `cap` entries each
-template <class F, int ROWS = 2>
-__global__ void __launch_bounds__(128, 4) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+// MINB: resident blocks per SM the register budget is sized for (4 -> 128 registers, 3 -> 168, 2 -> 255)
+template <class F, int ROWS = 2, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                     const uint32_t* __restrict__ order, uint32_t nbuckets_total, uint32_t cap,
                                                     int add_to_existing, XYZZ<F>* __restrict__ buckets) {

@@ -380,3 +380,42 @@ def test_device_api_two_streams_stress(product, oracle_c):
         for r in range(6):
             assert bytes(outs[t][r].cpu().numpy()) == wants[t], (t, r)
             assert int(sts[t][r].item()) == -1
+
+
+# ------------------------------------------------------------------------------------------------
+# checked MULTIEXP: subgroup check + the GLV / mod-r fast path it makes legal
+# ------------------------------------------------------------------------------------------------
+def test_checked_msm_glv_fast_path_matches_oracle(product, oracle_c):
+    """bls12_b200_set_checked_msm(1): inputs are proven to lie in G1 / G2, scalars are reduced mod r and split
+    k = q z^2 + t, the pipeline runs 2n points with 128-bit scalars.  On subgroup inputs the bytes must equal the
+    plain path and the oracle, for ordinary and for edge scalars; a point outside the subgroup gives code 2."""
+    z2 = 0xd201000000010000 ** 2
+    edge = [0, 1, 2, po.R - 1, po.R, po.R + 1, 2 * po.R, 2 * po.R + 5, 2 ** 256 - 1, 2 ** 255, z2 - 1, z2, z2 + 1, 7 * z2,
+            (po.R // z2) * z2, (po.R // z2) * z2 - 1, 2 ** 128 - 1, 2 ** 128, 2 ** 127]
+    rng = wl.SplitMix64(0x2537 + 84)
+    order3 = po.encode_g1((0, 2))
+    try:
+        for group, gen, name, plen in ((1, oracle_c.g1_gen_mul, "g1multiexp", 128), (2, oracle_c.g2_gen_mul, "g2multiexp", 256)):
+            fn = product.G1Multiexp if group == 1 else product.G2Multiexp
+            for n in ((1, 2, 5, len(edge), 300, 1000) if group == 1 else (1, 3, len(edge), 120)):
+                pts = [gen(rng.below(po.R - 1) + 1) for _ in range(n)]
+                ks = [edge[i] if n == len(edge) else rng.scalar256() for i in range(n)]
+                data = b"".join(p + k.to_bytes(32, "big") for p, k in zip(pts, ks))
+                err, ref = oracle_c.call(name, data)
+                assert err == 0
+                product.set_checked_msm(False)
+                assert fn(data) == ref
+                product.set_checked_msm(True)
+                assert fn(data) == ref, (group, n)
+        # streamed host chunks (6 chunks at 2^18) through the GLV path, closed form
+        n = (1 << 18) + 3
+        data, s = wl.g1_msm_input(n, 0x8484)
+        product.set_checked_msm(True)
+        assert product.G1Multiexp(data) == oracle_c.g1_gen_mul(s)
+        # a point of order 3 is on the curve but outside G1: code 2 in checked mode, accepted otherwise
+        bad = G1B + ONES + order3 + ONES
+        assert product.raw_call_into("bls12_g1multiexp", bad, 128) == (2, bytes([SENTINEL]) * 128)
+        product.set_checked_msm(False)
+        assert product.raw_call("bls12_g1multiexp", bad, 128)[0] == 0
+    finally:
+        product.set_checked_msm(False)
