@@ -42,6 +42,9 @@ sys.path.insert(0, ROOT)
 R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 FME_MAC32 = 300          # one 381-bit Montgomery multiplication = 2N^2+N = 300 32x32->64 MACs (N = 12)
 DECODE_FME = 2256        # pairing: decode + G1/G2 subgroup checks per pair (Jacobian ladders); counted on the host-emulation build
+G2_LADDER_FME = 1164     # ... of which the G2 membership ladder, which the dot-engine pipeline replaces by 12 Fp-mul in the line kernel
+                         # (tests/test_host_emul.py::test_deferred_g2_membership_agrees_with_the_ladder prints both)
+DOT_MAC = {"mul014": 12240, "sqr": 13536, "mul": 22608, "cyc": 6624}   # MAC32 per Fp12 operation of the dot engine (tables x 144 + 156 per output)
 MADD_FME = 10            # XYZZ mixed addition 8M + 2S (G1); G2: 8*3 + 2*2 = 28
 PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
 
@@ -577,20 +580,28 @@ def measure(ctx, workload, logn, calls, pairs, steps, warmup, window=0, cpu=True
             if hasattr(L, "bls12_b200_last_pairing_chunk"):
                 chunk = max(1, int(L.bls12_b200_last_pairing_chunk()))
             nch = [(k + chunk - 1) // chunk for k in ks]
-            fme = {"decode": DECODE_FME * sum(ks), "lines": 1780 * sum(ks), "accumulate": 2652 * sum(ks) + 2232 * sum(nch),
+            # this batch size runs the dot-engine pipeline: G2 membership is decided in the line kernel
+            fme = {"decode": (DECODE_FME - G2_LADDER_FME) * sum(ks), "lines": (1780 + 12) * sum(ks), "accumulate": 2652 * sum(ks) + 2232 * sum(nch),
                    "calls": sum(7688 + 54 * (c - 1) for c in nch)}
+            # multiply-accumulates the dot-engine kernels really execute (more than the Karatsuba count: one reduction per output instead)
+            actual_mac = {"accumulate": DOT_MAC["mul014"] * 68 * sum(ks) + DOT_MAC["sqr"] * 63 * sum(nch),
+                          "calls": sum(DOT_MAC["cyc"] * 316 + DOT_MAC["mul"] * (37 + c - 1) for c in nch)}
             extra["pairs_per_chunk"] = chunk
             peak_mac = ctx.measured_peak_mac()
             if stage:
                 avg = np.mean(np.asarray(stage), axis=0)
                 extra["stage_ms"] = {"decode_subgroup": float(avg[0]), "lines": float(avg[1]), "accumulate": float(avg[2]), "final_exp": float(avg[3])}
                 extra["stage_frac_of_peak"] = {k: fme[k] * FME_MAC32 / (float(avg[i]) * 1e-3) / peak_mac for i, k in enumerate(("decode", "lines", "accumulate", "calls"))}
+                extra["stage_actual_mac_frac"] = {"accumulate": actual_mac["accumulate"] / (float(avg[2]) * 1e-3) / peak_mac,
+                                                  "final_exp": actual_mac["calls"] / (float(avg[3]) * 1e-3) / peak_mac}
                 achieved = fme["accumulate"] * FME_MAC32 / (float(avg[2]) * 1e-3)
                 traffic, traffic_src = latest_traffic("k_pairing_accumulate_%d" % calls)
-                roofline = {"bound": "int32-mad", "kernel": "k_pairing_accumulate", "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
+                roofline = {"bound": "int32-mad", "kernel": "k_pairing_accumulate_dot6", "achieved": achieved / 1e12, "peak": peak_mac / 1e12,
                             "unit": "TMAC32/s", "frac": achieved / peak_mac, "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": PEAK_SOURCE,
-                            "algorithmic": "%d Fp-mul x 300 MAC32 (Karatsuba-tower count of the same products, host-emulation build)" % fme["accumulate"],
+                            "algorithmic": "%d Fp-mul x 300 MAC32: Karatsuba-tower count (2652 per pair + 2232 per chunk of %d pairs) of the products the kernel forms" % (fme["accumulate"], chunk),
+                            "actual_mac_frac": actual_mac["accumulate"] / (float(avg[2]) * 1e-3) / peak_mac,
+                            "algorithmic_line_bytes": 68 * 288 * sum(ks),
                             "whole_step_frac": sum(fme.values()) * FME_MAC32 / (dev_ms / steps * 1e-3) / peak_mac}
 
         # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload

@@ -148,7 +148,7 @@ __global__ void __maxnreg__(BLOCKS == 3 ? 112 : 80) k_pairing_accumulate_dot6(
       uint32_t* dst = dot_smem + (cur ^ (uint32_t)DOT6_F_WORDS) + lane;
 #pragma unroll 1
       for (int q = 0; q < 2; q++) {
-        const int c = 2 * role + q;
+        const int c = dot::role_comp(op, role, q);
         Fp r = dot::dot_eval_smem(dot::op_row(op, c), dot::op_count(op, c), F, G);
         if (!active) r = F.load(c);
 #pragma unroll
@@ -248,9 +248,9 @@ __global__ void __maxnreg__(112) k_pairing_final_dot6(size_t n_calls, const unsi
       uint32_t* dst = dot_smem + d * DOT6_F_WORDS + lane;
 #pragma unroll 1
       for (int q = 0; q < 2; q++) {
-        const int c = 2 * role + q;
+        const int c = dot::role_comp(op, role, q);
         Fp r = dot::dot_eval_smem(dot::op_row(op, c), dot::op_count(op, c), F, G);
-        if (opc == FX_CYC) r = dot::cyc_epilogue(r, F.load(c), (role & 1) != 0);
+        if (opc == FX_CYC) r = dot::cyc_epilogue(r, F.load(c), ((c >> 1) & 1) != 0);
 #pragma unroll
         for (int l = 0; l < 12; l++) dst[(c * 12 + l) * 32] = r.v[l];
       }

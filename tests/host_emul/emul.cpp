@@ -311,6 +311,38 @@ int emul_dot12_check(const unsigned char* in) {
   }
   return bad;
 }
+// Deferred G2 membership (pairing_dot.cuh k_pairing_lines_slots): walk T = [|z|]Q with the Miller-loop step formulas
+// and test psi(Q) == -T; Z = 0 at the end flags an exceptional chain (exact ladder decides).
+// returns bit 0: member according to the walk (or the ladder after an exceptional chain), bit 1: chain was exceptional;
+// counts[0] = Fp-mul of the exact ladder test, counts[1] = Fp-mul of the deferred comparison alone
+int emul_g2_membership_deferred(unsigned long long* counts, const unsigned char* in256) {
+  uint32_t w[64];
+  load_words(w, in256, 64);
+  G2Affine q;
+  if (decode_point(q, w) != 0) return -1;
+  if (is_inf(q)) return 1;
+  unsigned long long c0 = g_fp_mul_count;
+  const bool exact = g2_in_subgroup(q);
+  counts[0] = g_fp_mul_count - c0;
+  G2Proj t; t.x = q.x; t.y = q.y; t.z = fp2_one();
+  Fp2 l0, l1, l4;
+  for (int i = 62; i >= 0; i--) {
+    ml_dbl_step(t, l0, l1, l4);
+    if ((B200_Z_ABS >> i) & 1) ml_add_step(t, q, l0, l1, l4);
+  }
+  c0 = g_fp_mul_count;
+  bool member;
+  int exceptional = 0;
+  if (is_zero(t.z)) { member = exact; exceptional = 2; }
+  else {
+    const Fp2 px = mulo(conj(q.x), fp2_load_const(C_PSI_CX()));
+    const Fp2 py = mulo(conj(q.y), fp2_load_const(C_PSI_CY()));
+    member = eq(mulo(px, t.z), t.x) && eq(mulo(py, t.z), neg(t.y));
+  }
+  counts[1] = g_fp_mul_count - c0;
+  if (member != exact) return -2;          // the two tests must agree on EVERY point of E'(Fp2)
+  return (member ? 1 : 0) | exceptional;
+}
 int emul_g1_in_subgroup(const unsigned char* in128) {
   uint32_t w[32]; load_words(w, in128, 32);
   G1Affine p; int code = decode_point(p, w);

@@ -274,7 +274,7 @@ def test_plain_c_abi_multi_gpu_program():
     res = subprocess.run([exe, "19", "0"], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     line = json.loads(res.stdout.strip().splitlines()[-1])
-    assert line["ok"] and line["g1_equal"] and line["g2_equal"] and line["devices_used"] == line["gpus"]
+    assert line["ok"] and line["g1_equal"] and line["g2_equal"] and line["devices_used"] == line["devices_expected"]
     assert (line["late_error_code"], line["first_error_code"], line["out_untouched"]) == (1, 3, True)
 
 

@@ -133,6 +133,52 @@ def test_pairing_fme_constants(emul, oracle_c):
     assert list(c6) == [10, 23, 9, 28, 64, 24]     # madd, dbl+add, dbl over Fp / Fp2
 
 
+def test_deferred_g2_membership_agrees_with_the_ladder(emul, oracle_c):
+    """The dot-engine pipeline decides G2 membership from the Miller-loop walk T = [|z|]Q (pairing_dot.cuh).  It must agree
+    with the exact ladder test on members, on random points of E'(Fp2) outside G2 and on points of small order (13, 23),
+    where the incomplete step formulas go through their exceptional cases."""
+    import random as _r
+    rnd = _r.Random(0x2537 + 77)
+    h2 = 0x5d543a95414e7f1091d50792876a202cd91de4547085abaa68a205b2e5a7ddfa628f1cb4d9e82ef21537e293a6691ae1616ec6e786f0c70cf1c38e31c7238e5
+
+    def random_point():
+        while True:
+            x = (rnd.randrange(o.P), rnd.randrange(o.P))
+            rhs = o.f2_add(o.f2_mul(o.f2_sqr(x), x), (4, 4))
+            n = (rhs[0] * rhs[0] + rhs[1] * rhs[1]) % o.P
+            s = pow(n, (o.P + 1) // 4, o.P)
+            if s * s % o.P != n:
+                continue
+            for sg in (s, -s % o.P):
+                u = (rhs[0] + sg) * o.INV2 % o.P
+                xr = pow(u, (o.P + 1) // 4, o.P)
+                if xr and xr * xr % o.P == u:
+                    y = (xr, rhs[1] * o.fp_inv(2 * xr % o.P) % o.P)
+                    if o.f2_sqr(y) == rhs:
+                        return (x, y)
+    c = (ctypes.c_ulonglong * 2)()
+    seen = set()
+    members = [oracle_c.g2_gen_mul(rnd.randrange(1, o.R)) for _ in range(4)]
+    outside = [o.encode_g2(random_point()) for _ in range(4)]
+    small = []
+    base = random_point()
+    for ell in (13, 23):
+        pt = o.ec_mul(o.F2_OPS, (h2 * o.R) // (ell * ell), base)
+        if pt is not None:
+            for k in (1, 2, 5):
+                small.append(o.encode_g2(o.ec_mul(o.F2_OPS, k, pt)))
+    assert small
+    mixed = [o.encode_g2(o.ec_add(o.F2_OPS, o.decode_g2(members[0])[1], o.decode_g2(s)[1])) for s in small[:2]]   # member + small order
+    for enc in members + outside + small + mixed:
+        rc = emul.emul_g2_membership_deferred(c, enc)
+        assert rc >= 0, rc
+        assert (rc & 1) == (1 if oracle_c.lib().oracle_g2_in_subgroup(enc, 1) else 0)
+        seen.add(rc)
+    assert 1 in seen and 0 in seen            # members and non-members through the plain comparison
+    assert c[1] in (9, 12)                    # three or four Fp2 products: what the deferred test adds to the line kernel
+    print("exact ladder: %d Fp-mul, deferred comparison: %d, return codes seen: %s" % (c[0], c[1], sorted(seen)))
+
+
 def test_coop12_operation_tables(emul):
     """The warp-cooperative Fp12 operation tables (coop12.cuh), executed sequentially, equal the thread-level functions."""
     rnd = random.Random(12)

@@ -102,6 +102,35 @@ if "check" in what:
         assert int(d_codes.abs().sum().item()) == 0
         print("G1 batched decode%s over a 2^20-pair MULTIEXP input: %.3f ms -> %.3e points/s" % (" + subgroup check" if sub else "", ev0.elapsed_time(ev1), n / (ev0.elapsed_time(ev1) * 1e-3)), flush=True)
 
+if "checked" in what:
+    # opt-in checked MULTIEXP (subgroup check per point + GLV / mod-r fast path) against the plain path, host buffers
+    n = 1 << 20
+    data = gen_g1(n)
+    h = torch.from_numpy(data).pin_memory()
+    ref = b.G1Multiexp(h)
+    for label, checked, noglv in (("plain (reference semantics)", False, "0"), ("checked, GLV fast path", True, "0")):
+        b.set_checked_msm(checked)
+        for rep in range(3):
+            t0 = time.time(); out = b.G1Multiexp(h); dt = time.time() - t0
+        assert out == ref
+        print("G1 MULTIEXP 2^20 %s: %.2f ms end to end -> %.3e points/s" % (label, dt * 1e3, n / dt), flush=True)
+    b.set_checked_msm(False)
+    L.bls12_b200_set_profile(1)
+    d_in = h.cuda()
+    d_part = torch.zeros(512, dtype=torch.uint8, device="cuda")
+    d_st = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+    st = (ctypes.c_float * 4)()
+    nz = ctypes.c_uint64()
+    for checked in (False, True):
+        b.set_checked_msm(checked)
+        for rep in range(2):
+            L.bls12_b200_msm_partial_device(1, d_in.data_ptr(), n, 0, d_part.data_ptr(), d_st.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        L.bls12_b200_last_msm_profile(st, ctypes.byref(nz))
+        print("  stages (checked=%s): decode[+check]+sort %.2f, accumulate %.2f, reduce %.2f, combine %.2f ms; %d additions" % (checked, st[0], st[1], st[2], st[3], nz.value), flush=True)
+    b.set_checked_msm(False)
+    L.bls12_b200_set_profile(0)
+
 if "batch" in what:
     for k in (4, 32, 128):
         ncalls = 16384 if k <= 32 else 4096
