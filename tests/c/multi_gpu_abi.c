@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
   int expect_devices = (int)(n >> 17) < ngpu ? (int)(n >> 17) : ngpu;
   if (expect_devices < 1) expect_devices = 1;
   ok = ok && same1 && same2 && devices_used == expect_devices && late_only == EIP2537_POINT_NOT_ON_CURVE && both == EIP2537_INVALID_ELEMENT && untouched;
-  printf("{\"test\": \"multi_gpu_abi\", \"pairs\": %zu, \"gpus\": %d, \"devices_used\": %d, \"g1_equal\": %s, \"g2_equal\": %s, "
+  printf("{\"test\": \"multi_gpu_abi\", \"pairs\": %zu, \"gpus\": %d, \"devices_used\": %d, \"devices_expected\": %d, \"g1_equal\": %s, \"g2_equal\": %s, "
          "\"late_error_code\": %d, \"first_error_code\": %d, \"out_untouched\": %s, \"ms_1gpu\": %.2f, \"ms_ngpu\": %.2f, \"ok\": %s}\n",
          n, ngpu, devices_used, expect_devices, same1 ? "true" : "false", same2 ? "true" : "false", (int)late_only, (int)both,
          untouched ? "true" : "false", ms_single, ms_multi, ok ? "true" : "false");
