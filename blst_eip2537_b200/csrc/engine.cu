@@ -126,6 +126,11 @@ struct Engine {
   cudaStream_t stream2 = nullptr;            // H2D copies of streamed MSM chunks (overlap with accumulation)
   cudaEvent_t ev_group[8] = {};
   cudaEvent_t ev_tail = nullptr;
+  // timing of the last streamed MSM (events with timing): when the H2D copies took a large share of the call -- several
+  // ranks sharing the host's memory bandwidth -- the next call uses a chunk schedule whose LAST chunks are small
+  cudaEvent_t ev_copy[2] = {}, ev_span[2] = {};
+  bool span_valid = false;
+  bool copy_bound = false;
   // asynchronous (device-resident) submissions return while their kernels still use the buffers below: `busy` is
   // recorded on the caller's stream at the end of each of them; the next user of the workspace orders itself after it
   cudaEvent_t busy = nullptr;
@@ -185,6 +190,7 @@ static void engine_destroy(Engine* e) {
   for (int k = 0; k < 8; k++) if (e->ev_group[k]) cudaEventDestroy(e->ev_group[k]);
   if (e->ev_tail) cudaEventDestroy(e->ev_tail);
   if (e->busy) cudaEventDestroy(e->busy);
+  for (int k = 0; k < 2; k++) { if (e->ev_copy[k]) cudaEventDestroy(e->ev_copy[k]); if (e->ev_span[k]) cudaEventDestroy(e->ev_span[k]); }
   delete e;
 }
 
@@ -201,6 +207,7 @@ static int engine_create(DevicePool& pool, Engine** out) {
   for (int k = 0; k < 8 && err == cudaSuccess; k++) err = cudaEventCreateWithFlags(&e->ev_group[k], cudaEventDisableTiming);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_tail, cudaEventDisableTiming);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->busy, cudaEventDisableTiming);
+  for (int k = 0; k < 2 && err == cudaSuccess; k++) { err = cudaEventCreate(&e->ev_copy[k]); if (err == cudaSuccess) err = cudaEventCreate(&e->ev_span[k]); }
   if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_out, 4096);
   if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_status, 64);
   if (err != cudaSuccess) {
@@ -631,12 +638,29 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
   // every later copy is shorter than the accumulation of the chunk before it.  B200_STREAM_EVEN=1 restores 8 equal chunks.
   static const int even_env = getenv("B200_STREAM_EVEN") ? atoi(getenv("B200_STREAM_EVEN")) : 0;
   static const int cuts_geo[] = {0, 1, 2, 4, 8, 16, 32};
+  static const int cuts_sym[] = {0, 1, 3, 7, 15, 23, 28, 31, 32};       // 1 2 4 8 8 5 3 1: small FIRST and LAST chunks
   static const int cuts_even8[] = {0, 4, 8, 12, 16, 20, 24, 28, 32};
   static const int cuts_mid[] = {0, 4, 8, 16, 32};
   static const int cuts_one[] = {0, 32};
+  // Copy-bound regime (measured on the previous streamed call of this workspace: the copies took > 40 % of the call, e.g.
+  // 8 ranks sharing the host's ~186 GB/s): what follows the LAST copy is exposed, so the last chunks must be small.
+  static const int sched_env = getenv("B200_STREAM_SCHEDULE") ? atoi(getenv("B200_STREAM_SCHEDULE")) : 0;   // 1 geometric, 2 symmetric
+  if (e.span_valid && !sched_env) {
+    float copy_ms = 0, span_ms = 0;
+    if (cudaEventElapsedTime(&copy_ms, e.ev_copy[0], e.ev_copy[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&span_ms, e.ev_span[0], e.ev_span[1]) == cudaSuccess && span_ms > 0)
+      e.copy_bound = copy_ms > 0.4f * span_ms;
+    else
+      (void)cudaGetLastError();
+  }
+  e.span_valid = false;
   const int* cuts = cuts_one;
   int nchunks = 1;
-  if (n >= (1u << 18)) { if (even_env) { cuts = cuts_even8; nchunks = 8; } else { cuts = cuts_geo; nchunks = 6; } }
+  if (n >= (1u << 18)) {
+    if (even_env) { cuts = cuts_even8; nchunks = 8; }
+    else if (sched_env == 2 || (sched_env == 0 && e.copy_bound)) { cuts = cuts_sym; nchunks = 8; }
+    else { cuts = cuts_geo; nchunks = 6; }
+  }
   else if (n >= (1u << 16)) { cuts = cuts_mid; nchunks = 4; }
   size_t chunk_cap = 0;
   for (int c = 0; c < nchunks; c++) {
@@ -646,6 +670,12 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
   MsmRun<F> r;
   if ((rc = msm_begin<F>(e, r, n, chunk_cap))) return rc;
   CUDA_TRY(cudaMemsetAsync(e.status.ptr, 0xFF, 8, s));
+  const bool timed = nchunks > 1 && n >= (1u << 18);
+  if (timed) {
+    CUDA_TRY(cudaEventRecord(e.ev_span[0], s));
+    CUDA_TRY(cudaStreamWaitEvent(cs, e.ev_span[0], 0));       // the copies of this call start with the call
+    CUDA_TRY(cudaEventRecord(e.ev_copy[0], cs));
+  }
   bool first = true;
   for (int c = 0; c < nchunks; c++) {
     const size_t lo = n * cuts[c] / 32, hi = n * cuts[c + 1] / 32;
@@ -658,10 +688,16 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
       CUDA_TRY(cudaEventRecord(e.ev_group[c], cs));
       CUDA_TRY(cudaStreamWaitEvent(s, e.ev_group[c], 0));
     }
+    if (timed && c == nchunks - 1) CUDA_TRY(cudaEventRecord(e.ev_copy[1], cs));
     if ((rc = msm_feed<F>(e, r, (const uint32_t*)dst, hi - lo, index_base + lo, first, (unsigned long long*)e.status.ptr, s))) return rc;
     first = false;
   }
-  return msm_tail<F>(e, r, dst_partial ? dst_partial : (XYZZ<F>*)e.partial.ptr, (unsigned long long*)e.status.ptr, dst_status, s);
+  rc = msm_tail<F>(e, r, dst_partial ? dst_partial : (XYZZ<F>*)e.partial.ptr, (unsigned long long*)e.status.ptr, dst_status, s);
+  if (!rc && timed) {
+    CUDA_TRY(cudaEventRecord(e.ev_span[1], s));
+    e.span_valid = true;       // every caller synchronises e.stream before the workspace is leased again
+  }
+  return rc;
 }
 
 // finish a host call on workspace e: partial sum(s) -> affine -> bytes; `out` is written only on success

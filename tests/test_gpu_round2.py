@@ -352,6 +352,29 @@ def test_pageable_and_pinned_inputs_agree(product, oracle_c):
     assert product.raw_call_into("bls12_g1multiexp", bytes(bad), 128) == (1, bytes([0xA5]) * 128)
 
 
+def test_symmetric_chunk_schedule_in_a_fresh_process(oracle_c):
+    """B200_STREAM_SCHEDULE=2 forces the 8-chunk schedule the engine switches to by itself when the H2D copies dominate a
+    call (several ranks sharing the host): same bytes, and an error in the small LAST chunk is still reported."""
+    import subprocess
+    n = (1 << 18) + 4321
+    data, s = wl.g1_msm_input(n, 0x6262)
+    want = oracle_c.g1_gen_mul(s)
+    path = os.path.join(ROOT, "gpurun_out", "_sched_input.bin")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    bad = bytearray(data)
+    bad[160 * (n - 2) + 127] ^= 1
+    with open(path, "wb") as fh:
+        fh.write(data + bytes(bad))
+    code = ("import sys; sys.path.insert(0, %r); import blst_eip2537_b200 as b; d = open(%r, 'rb').read(); h = len(d) // 2; "
+            "print(b.G1Multiexp(d[:h]).hex()); print(b.G1Multiexp(d[:h]).hex()); print(b.raw_call('bls12_g1multiexp', d[h:], 128)[0])" % (ROOT, path))
+    env = dict(os.environ, B200_STREAM_SCHEDULE="2")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    os.remove(path)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.split()
+    assert lines == [want.hex(), want.hex(), "1"]
+
+
 def test_device_api_two_streams_stress(product, oracle_c):
     """Asynchronous device-resident submissions from two CUDA streams (and a host call in between) must not share
     scratch memory in flight (workspaces were shared and the mutex dropped after enqueue)."""
