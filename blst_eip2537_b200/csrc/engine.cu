@@ -469,46 +469,54 @@ static int msm_feed(Engine& e, MsmRun<F>& r, const uint32_t* d_raw, size_t n, ui
   return E_SUCCESS;
 }
 
-// bucket-reduction tree (leaf folds 2^L0_log buckets, inner levels fold up to 8 children), then the
-// Horner combine of the window sums.  (Overlapping this latency-bound tail with the accumulation of
-// other windows on a second stream was tried and measured slower: 11.7 vs 10.7 ms for 2^20 G1 -- the
-// dependent chains need the multiply pipe to themselves.)
+// Bucket reduction (leaf threads fold 2^L0_log buckets by running sums; the levels above only ADD vectors of partial sums and
+// one walk per window scales them, msm.cuh k_reduce_level / k_window_finish), then the Horner combine of the window sums.
+// (Overlapping this latency-bound tail with the accumulation of other windows on a second stream was tried and measured
+// slower: 11.7 vs 10.7 ms for 2^20 G1 -- the dependent chains need the multiply pipe to themselves.)
 template <class F>
 static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, const unsigned long long* d_status, unsigned long long* d_status_copy,
                     cudaStream_t s) {
   const MsmPlan& plan = r.plan;
   int rc;
   static const int leaf_env = getenv("B200_LEAF_LOG") ? atoi(getenv("B200_LEAF_LOG")) : 0;
-  // Buckets per leaf thread (log2), measured per size (profiles/r01_bench.md): small MSMs have few buckets and the
-  // leaf level is pure latency (2 dependent point additions per bucket), so short leaves win; large ones want
-  // fewer, longer leaves (8 buckets for G1, 16 for G2) to keep the cooperative upper levels small.
+  // Buckets per leaf thread (log2), measured per size (profiles/r02_msm_tail.md): small MSMs have few buckets and the
+  // leaf level is pure latency (2 dependent point additions per bucket), so short leaves win; large ones are
+  // throughput-bound and 8 buckets per thread cost the fewest additions (14 per 8 buckets).
   const size_t total_buckets = (size_t)plan.nwin * plan.nb;
-  int L0_auto = total_buckets < (1u << 14) ? 1 : (total_buckets < (1u << 16) ? 2 : 3);
-  if (sizeof(F) != sizeof(Fp) && total_buckets >= (1u << 18)) L0_auto = 4;
+  const int L0_auto = total_buckets < (1u << 14) ? 1 : (total_buckets < (1u << 16) ? 2 : 3);
   int L0_want = leaf_env > 0 ? leaf_env : L0_auto;
   int L0_log = plan.log_nb < L0_want ? plan.log_nb : L0_want;
   size_t nodes_per_win = plan.nb >> L0_log;
-  if ((rc = e.nodes_a.reserve((size_t)plan.nwin * nodes_per_win * sizeof(Node<F>)))) return rc;
-  if ((rc = e.nodes_b.reserve((size_t)plan.nwin * (nodes_per_win / 2 + 1) * sizeof(Node<F>)))) return rc;
-  Node<F>* cur = (Node<F>*)e.nodes_a.ptr;
-  Node<F>* nxt = (Node<F>*)e.nodes_b.ptr;
+  static const int inner_env = getenv("B200_INNER_LOG") ? atoi(getenv("B200_INNER_LOG")) : 0;
+  // two children per level: one dependent addition per level and one more component per node (measured against four: 1.30 vs 1.42 ms)
+  const ReduceLevels lv = make_reduce_levels(plan.log_nb, L0_log, inner_env > 0 ? inner_env : 1);
+  // node vectors of XYZZ sums: the leaves write (s, w); level i adds 2^l_log - 1 components and has 2^l_log times fewer nodes
+  const size_t node_words = (size_t)plan.nwin * (2 * nodes_per_win + REDUCE_MAX_LEVELS * 8) * sizeof(XYZZ<F>);
+  if ((rc = e.nodes_a.reserve(node_words))) return rc;
+  if ((rc = e.nodes_b.reserve(node_words + (size_t)plan.nwin * sizeof(XYZZ<F>)))) return rc;
+  XYZZ<F>* cur = (XYZZ<F>*)e.nodes_a.ptr;
+  XYZZ<F>* nxt = (XYZZ<F>*)e.nodes_b.ptr;
   LAUNCH(k_reduce_leaf<F>, blocks_for(plan.nwin * nodes_per_win, 128), 128, s, r.buckets,
-         (uint32_t)(plan.nwin * nodes_per_win), 1 << L0_log, cur);
-  int log_cov = L0_log;                  // log2(buckets covered per node)
-  while (nodes_per_win > 1) {
-    int remaining_log = plan.log_nb - log_cov;
-    static const int inner_env = getenv("B200_INNER_LOG") ? atoi(getenv("B200_INNER_LOG")) : 0;
-    const int inner_want = inner_env > 0 ? inner_env : 2;   // children per node = 4; measured: 2 beats 3 by 0.5-1.6 % (G1 2^16..2^20, G2 2^18), 1 and 4 lose
-    int l_log = remaining_log < inner_want ? remaining_log : inner_want;
-    size_t out_per_win = nodes_per_win >> l_log;
-    LAUNCH(k_reduce_inner<F>, blocks_for(plan.nwin * out_per_win * Coop<F>::LANES, 128), 128, s, cur,
-           (uint32_t)(plan.nwin * out_per_win), 1 << l_log, log_cov, nxt);
-    Node<F>* tmp = cur; cur = nxt; nxt = tmp;
+         (uint32_t)(plan.nwin * nodes_per_win), 1 << L0_log, (Node<F>*)cur);
+  int K = 2;
+  for (int i = 0; i < lv.n; i++) {
+    const int l_log = lv.l_log[i], K_out = K + (1 << l_log) - 1;
+    const size_t out_per_win = nodes_per_win >> l_log;
+    const size_t comps = (size_t)plan.nwin * out_per_win * K_out;
+    // lane groups pay only where a level is latency-bound (a group spends 32 / 128 multiplication slots on an addition that costs a
+    // thread 14 / 42): measured crossover, profiles/r02_msm_tail.md
+    static const size_t coop_env = getenv("B200_REDUCE_COOP_BELOW") ? (size_t)atol(getenv("B200_REDUCE_COOP_BELOW")) : 0;
+    const size_t coop_below = coop_env ? coop_env : (sizeof(F) == sizeof(Fp) ? 8192 : 6144);
+    if (comps >= coop_below) LAUNCH((k_reduce_level<F, false>), blocks_for(comps, 128), 128, s, cur, K, (uint32_t)(plan.nwin * out_per_win), l_log, nxt);
+    else                     LAUNCH((k_reduce_level<F, true>), blocks_for(comps * Coop<F>::LANES, 128), 128, s, cur, K, (uint32_t)(plan.nwin * out_per_win), l_log, nxt);
+    XYZZ<F>* tmp = cur; cur = nxt; nxt = tmp;
     nodes_per_win = out_per_win;
-    log_cov += l_log;
+    K = K_out;
   }
+  XYZZ<F>* tw = (XYZZ<F>*)((char*)e.nodes_b.ptr + node_words);      // T_w of every window, behind the node vectors
+  LAUNCH(k_window_finish<F>, (unsigned)plan.nwin, 8 * Coop<F>::LANES, s, cur, K, lv, tw);
   g_stage.mark(3, s);
-  LAUNCH(k_window_combine<F>, 1, 32, s, cur, plan, d_partial, d_status, d_status_copy);
+  LAUNCH(k_window_combine<F>, 1, 32, s, tw, plan, d_partial, d_status, d_status_copy);
   g_stage.mark(4, s);
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
@@ -1643,6 +1651,25 @@ __global__ void __launch_bounds__(256) k_dot_chain(int iters, Fp* out) {
   else if (x.v[0] == 0xdeadbeefu && x.v[5] == 0x12345u) out[blockIdx.x] = x;
 }
 
+// ONE double-width product + separated reduction per dependent step: the low-latency form of a field multiplication
+// (the product rows are independent carry chains; only the reduction rows are serial)
+template <class ACC>
+__global__ void __launch_bounds__(256) k_ll_chain(int iters, Fp* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fp x = fp_one(), y = fp_load_const(C_G1GEN());
+  x.v[0] ^= (uint32_t)i;
+  x = fp_reduce_once(x, 0);
+#pragma unroll 1
+  for (int k = 0; k < iters; k++) {
+    ACC A;
+    dot::acc_zero(A);
+    dot::acc_product(A, x, y);
+    x = dot::acc_reduce(A, 1);
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = x;
+  else if (x.v[0] == 0xdeadbeefu && x.v[5] == 0x12345u) out[blockIdx.x] = x;
+}
+
 extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, float* ms, byte* digest48) {
   Lease lease;
   int rc = lease.acquire(-1);
@@ -1668,6 +1695,8 @@ extern "C" EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, in
     else if (mode == 11) LAUNCH(k_fp_chain_v<5>, nblk, 256, s, iters, (Fp*)e.pts.ptr);
     else if (mode == 12) LAUNCH(k_fp_chain_v<6>, nblk, 256, s, iters, (Fp*)e.pts.ptr);
     else if (mode == 5) LAUNCH(k_dot_chain<dot::Acc64>, nblk, 256, s, iters, (Fp*)e.pts.ptr);
+    else if (mode == 13) LAUNCH(k_ll_chain<dot::Acc64>, nblk, 256, s, iters, (Fp*)e.pts.ptr);
+    else if (mode == 14) LAUNCH(k_ll_chain<dot::Acc>, nblk, 256, s, iters, (Fp*)e.pts.ptr);
     else                LAUNCH(k_imad32_peak, nblk, 256, s, iters, (unsigned long long*)e.pts.ptr);
     CUDA_TRY2(cudaEventRecord(t1, s));
     CUDA_TRY2(cudaStreamSynchronize(s));

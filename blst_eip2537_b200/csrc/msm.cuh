@@ -57,6 +57,30 @@ static inline MsmPlan make_plan(int c, int nbits = 256) {
   return p;
 }
 
+// Upper levels of the bucket reduction (k_reduce_level / k_window_finish): level i folds 2^l_log[i] children that cover
+// 2^cov[i] buckets each.  Four children per level (three dependent additions), two when an odd number of bits remains.
+static constexpr int REDUCE_MAX_LEVELS = 16;
+struct ReduceLevels {
+  int n;
+  uint8_t l_log[REDUCE_MAX_LEVELS], cov[REDUCE_MAX_LEVELS];
+};
+static inline ReduceLevels make_reduce_levels(int log_nb, int leaf_log, int inner_log = 2) {
+  ReduceLevels lv;
+  lv.n = 0;
+  int cov = leaf_log;
+  while (cov < log_nb) {
+    const int rem = log_nb - cov, l = rem < inner_log ? rem : inner_log;
+    lv.l_log[lv.n] = (uint8_t)l; lv.cov[lv.n] = (uint8_t)cov; lv.n++;
+    cov += l;
+  }
+  return lv;
+}
+static inline int reduce_root_width(const ReduceLevels& lv) {      // accumulators per root node
+  int k = 2;
+  for (int i = 0; i < lv.n; i++) k += (1 << lv.l_log[i]) - 1;
+  return k;
+}
+
 #ifdef __CUDACC__
 
 static constexpr unsigned long long STATUS_OK = ~0ull;
@@ -445,36 +469,94 @@ __global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fp) ? 4 : 2)) k_redu
   nodes[t].s = run;
   nodes[t].w = acc;
 }
-// inner level: fold L children, each covering 2^log_m buckets:
-//   s = sum s_t ;  w = sum w_t + 2^log_m * sum_t t*s_t   (t = 0..L-1)
-// These levels have few nodes and long dependency chains, so each node is folded by a group of
-// 8 lanes with the lane-cooperative point operations of coop.cuh.
-template <class F>
-__global__ void __launch_bounds__(128) k_reduce_inner(const Node<F>* __restrict__ in, uint32_t nout_total, int L, int log_m,
-                                                      Node<F>* __restrict__ out) {
-  const CoopGroup g = coop_group<F>();
-  uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) / Coop<F>::LANES;
-  if (t >= nout_total) return;
-  const Node<F>* ch = in + (size_t)t * L;
-  XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>(), wsum = xyzz_inf<F>();
-  for (int j = L - 1; j >= 0; j--) {
-    XYZZ<F> cw = ch[j].w;
-    coop_add(wsum, cw, g);
-    coop_add(acc, run, g);
-    XYZZ<F> cs = ch[j].s;
-    coop_add(run, cs, g);
+// Upper levels WITHOUT doublings.  Folding L children that cover 2^cov buckets each needs
+//   w_parent = sum_t w_t + 2^cov * sum_t t*s_t ;
+// round 1 evaluated this per node (a running sum plus `cov` doublings at every level: ~80 dependent additions and ~48
+// doublings from the leaves to the root, 1.1 of the 1.8 ms of this stage).  The scaled term is linear, so it can be
+// summed over ALL nodes of a level before it is scaled: a node carries a vector of plain sums
+//   acc[0] = s,  acc[1] = sum of the leaf w's,  then for every level i below it and t = 1..L_i-1:
+//   a_{i,t} = sum of s over the level-i children with index t
+// a level only ADDS vectors component-wise (one lane group per component: 3 dependent additions per level) and appends
+// its own a_{.,t} = s of child t; the root's  w + sum_i 2^cov_i * sum_t t*a_{i,t}  is one Horner walk per window
+// (k_window_finish: cov_top doublings in all).
+// COOP = false: one THREAD per component (the wide lower levels are throughput-bound, and a lane group spends 32 multiplication
+// slots on an addition a thread does in 14); COOP = true: one lane group per component (narrow upper levels: latency).
+template <class F, bool COOP>
+__global__ void __launch_bounds__(128) k_reduce_level(const XYZZ<F>* __restrict__ in, int K_in, uint32_t nout_total, int l_log,
+                                                      XYZZ<F>* __restrict__ out) {
+  const int L = 1 << l_log, K_out = K_in + L - 1;
+  const unsigned long long gid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / (COOP ? Coop<F>::LANES : 1);
+  if (gid >= (unsigned long long)nout_total * K_out) return;
+  const uint32_t t = (uint32_t)(gid / K_out);
+  const int k = (int)(gid % K_out);
+  const XYZZ<F>* ch = in + (size_t)t * L * K_in;
+  XYZZ<F> acc;
+  if (k < K_in) {
+    acc = ch[k];
+    if (COOP) {
+      const CoopGroup g = coop_group<F>();
+      for (int j = 1; j < L; j++) { XYZZ<F> c = ch[(size_t)j * K_in + k]; coop_add(acc, c, g); }
+    } else {
+      for (int j = 1; j < L; j++) { XYZZ<F> c = ch[(size_t)j * K_in + k]; xyzz_add(acc, c); }
+    }
+  } else {
+    acc = ch[(size_t)(k - K_in + 1) * K_in];      // a_{this level, t} = s of child t
   }
-  for (int k = 0; k < log_m; k++) coop_dbl(acc, g);
-  coop_add(wsum, acc, g);
-  if (g.lane == 0 && g.sub == 0) { out[t].s = run; out[t].w = wsum; }
+  if (COOP) {
+    const CoopGroup g = coop_group<F>();
+    if (g.lane != 0 || g.sub != 0) return;
+  }
+  out[(size_t)t * K_out + k] = acc;
+}
+// One block of 8 lane groups per window: groups form U_i = sum_t t*a_{i,t} in parallel, then group 0 walks
+// T = w + 2^cov_0 (U_0 + 2^(cov_1 - cov_0) (U_1 + ...)).
+template <class F>
+__global__ void k_window_finish(const XYZZ<F>* __restrict__ roots, int K, ReduceLevels lv, XYZZ<F>* __restrict__ tw) {
+  __shared__ XYZZ<F> U[REDUCE_MAX_LEVELS];
+  const CoopGroup g = coop_group<F>();
+  const int grp = threadIdx.x / Coop<F>::LANES, ngrp = blockDim.x / Coop<F>::LANES;
+  const XYZZ<F>* r = roots + (size_t)blockIdx.x * K;
+  int base = 2;
+  for (int i = 0; i < lv.n; i++) {
+    const int L = 1 << lv.l_log[i];
+    if (i % ngrp == grp) {
+      XYZZ<F> u;
+      if (L == 2) {
+        u = r[base];
+      } else if (L == 4) {                        // a1 + 2 a2 + 3 a3 = (a1 + a3) + 2 (a2 + a3)
+        XYZZ<F> a3 = r[base + 2], y = r[base];
+        u = r[base + 1];
+        coop_add(u, a3, g); coop_dbl(u, g);
+        coop_add(y, a3, g); coop_add(u, y, g);
+      } else {                                    // running sum from the top child down
+        XYZZ<F> run = xyzz_inf<F>();
+        u = xyzz_inf<F>();
+        for (int t = L - 1; t >= 1; t--) { XYZZ<F> a = r[base + t - 1]; coop_add(run, a, g); coop_add(u, run, g); }
+      }
+      if (g.lane == 0 && g.sub == 0) U[i] = u;
+    }
+    base += L - 1;
+  }
+  __syncthreads();
+  if (grp != 0) return;
+  XYZZ<F> acc = xyzz_inf<F>();
+  for (int i = lv.n - 1; i >= 0; i--) {
+    XYZZ<F> u = U[i];
+    coop_add(acc, u, g);
+    const int nd = lv.cov[i] - (i > 0 ? lv.cov[i - 1] : 0);
+    for (int k = 0; k < nd; k++) coop_dbl(acc, g);
+  }
+  XYZZ<F> w = r[1];
+  coop_add(acc, w, g);
+  if (g.lane == 0 && g.sub == 0) tw[blockIdx.x] = acc;
 }
 
-// Horner over the windows from the top down: acc = 2^width[w] * acc + T_w, T_w = roots[w].w.
+// Horner over the windows from the top down: acc = 2^width[w] * acc + T_w.
 // One cooperative lane group walks the ~240 sequential doublings.
 // The result (and, when asked, a copy of the shard's first-error key) may be written through a PEER pointer into
 // another GPU's gather buffer: the multi-GPU exchange is fused into this last kernel of the shard's pipeline.
 template <class F>
-__global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan, XYZZ<F>* __restrict__ acc_io,
+__global__ void k_window_combine(const XYZZ<F>* __restrict__ tw, MsmPlan plan, XYZZ<F>* __restrict__ acc_io,
                                  const unsigned long long* __restrict__ status_src, unsigned long long* __restrict__ status_dst) {
   if (blockIdx.x != 0 || threadIdx.x >= Coop<F>::LANES) return;
   if (threadIdx.x == 0 && status_dst) *status_dst = *status_src;
@@ -482,7 +564,7 @@ __global__ void k_window_combine(const Node<F>* __restrict__ roots, MsmPlan plan
   XYZZ<F> acc = xyzz_inf<F>();
   for (int w = plan.nwin - 1; w >= 0; w--) {
     for (int k = 0; k < plan.width[w]; k++) coop_dbl(acc, g);   // acc is still infinity for the top window
-    XYZZ<F> t = roots[w].w;
+    XYZZ<F> t = tw[w];
     coop_add(acc, t, g);
   }
   if (g.lane == 0 && g.sub == 0) *acc_io = acc;

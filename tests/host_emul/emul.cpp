@@ -113,20 +113,46 @@ static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, 
     for (int j = L - 1; j >= 0; j--) { xyzz_add(run, buckets[t * L + j]); xyzz_add(acc, run); }
     cur[t].s = run; cur[t].w = acc;
   }
-  int log_cov = L0_log;
-  while (npw > 1) {
-    int rem = plan.log_nb - log_cov, l_log = rem < 3 ? rem : 3, L = 1 << l_log;
-    size_t opw = npw >> l_log;
-    Node<F>* nxt = new Node<F>[plan.nwin * opw];
-    for (size_t t = 0; t < plan.nwin * opw; t++) {
-      XYZZ<F> run = xyzz_inf<F>(), acc = xyzz_inf<F>(), wsum = xyzz_inf<F>();
-      for (int j = L - 1; j >= 0; j--) { xyzz_add(wsum, cur[t * L + j].w); xyzz_add(acc, run); xyzz_add(run, cur[t * L + j].s); }
-      for (int q = 0; q < log_cov; q++) acc = xyzz_dbl(acc);
-      xyzz_add(wsum, acc);
-      nxt[t].s = run; nxt[t].w = wsum;
-    }
-    delete[] cur; cur = nxt; npw = opw; log_cov += l_log;
+  // upper levels as k_reduce_level / k_window_finish do them: vectors of plain sums, scaled once at the root
+  const ReduceLevels lv = make_reduce_levels(plan.log_nb, L0_log, 1 + (plan.c & 1));   // both level shapes get exercised
+  int K = 2;
+  XYZZ<F>* vec = new XYZZ<F>[plan.nwin * npw * 2];
+  for (size_t t = 0; t < plan.nwin * npw; t++) { vec[2 * t] = cur[t].s; vec[2 * t + 1] = cur[t].w; }
+  for (int i = 0; i < lv.n; i++) {
+    const int L = 1 << lv.l_log[i], K_out = K + L - 1;
+    const size_t opw = npw >> lv.l_log[i];
+    XYZZ<F>* nxt = new XYZZ<F>[plan.nwin * opw * K_out];
+    for (size_t t = 0; t < plan.nwin * opw; t++)
+      for (int k = 0; k < K_out; k++) {
+        const XYZZ<F>* ch = vec + t * L * K;
+        XYZZ<F> a;
+        if (k < K) { a = ch[k]; for (int j = 1; j < L; j++) xyzz_add(a, ch[(size_t)j * K + k]); }
+        else a = ch[(size_t)(k - K + 1) * K];
+        nxt[t * K_out + k] = a;
+      }
+    delete[] vec; vec = nxt; npw = opw; K = K_out;
   }
+  if (K != reduce_root_width(lv) || npw != 1) { delete[] vec; delete[] cur; delete[] buckets; return -100; }
+  for (int win = 0; win < plan.nwin; win++) {
+    const XYZZ<F>* r = vec + (size_t)win * K;
+    XYZZ<F> tacc = xyzz_inf<F>();
+    int base = 2;
+    XYZZ<F> U[REDUCE_MAX_LEVELS];
+    for (int i = 0; i < lv.n; i++) {
+      const int L = 1 << lv.l_log[i];
+      XYZZ<F> run = xyzz_inf<F>(), u = xyzz_inf<F>();
+      for (int t = L - 1; t >= 1; t--) { xyzz_add(run, r[base + t - 1]); xyzz_add(u, run); }
+      U[i] = u; base += L - 1;
+    }
+    for (int i = lv.n - 1; i >= 0; i--) {
+      xyzz_add(tacc, U[i]);
+      const int nd = lv.cov[i] - (i > 0 ? lv.cov[i - 1] : 0);
+      for (int q = 0; q < nd; q++) tacc = xyzz_dbl(tacc);
+    }
+    xyzz_add(tacc, r[1]);
+    cur[win].w = tacc;
+  }
+  delete[] vec;
   XYZZ<F> acc = xyzz_inf<F>();
   for (int win = plan.nwin - 1; win >= 0; win--) {
     for (int q = 0; q < plan.width[win]; q++) acc = xyzz_dbl(acc);

@@ -42,7 +42,8 @@ def gen_g1(n):
 
 if "latency" in what:
     # one warp per SM sub-partition at most: dependent Fp-mul chain latency, CIOS (rolled) vs product scanning
-    for mode, name in ((0, "mul (rolled CIOS)"),):
+    for mode, name in ((0, "mul (rolled CIOS)"), (7, "CIOS 4 rows/iter"), (8, "CIOS 6 rows/iter"), (9, "CIOS fully unrolled"),
+                       (13, "product + separated reduction, 64-bit pairs"), (14, "product + separated reduction, 32-bit words")):
         for nthr in (32, 148 * 128, 148 * 2048):
             iters = 2000
             L.bls12_b200_fp_microbench(mode, nthr, iters, ctypes.byref(ms), None)
