@@ -150,5 +150,88 @@ __device__ __noinline__ void coop_add(XYZZ<F>& acc, const XYZZ<F>& q, const Coop
   acc.x = x3; acc.y = sub(ya, yb); acc.zz = zz3; acc.zzz = zzz3;
 }
 
+// ---- homogeneous coordinates (ec.cuh Hom): two dependency levels per operation, no exceptional cases --------------------
+template <class F>
+__device__ __noinline__ void coop_hdbl(Hom<F>& p, const CoopGroup g) {
+  const int l = g.lane;
+  // level 1: t0 = Y^2, t1 = Y Z, t2 = Z^2, t3 = X Y
+  F a = p.y, b = p.y;
+  coop_pick(b, l == 1, p.z);
+  coop_pick(a, l == 2, p.z); coop_pick(b, l == 2, p.z);
+  coop_pick(a, l == 3, p.x);
+  const F r1 = coop_product(a, b, g);
+  const F t0 = coop_bcast(r1, 0, g), t1 = coop_bcast(r1, 1, g), t3 = coop_bcast(r1, 3, g);
+  const F t2 = mul_b3(coop_bcast(r1, 2, g));
+  const F z8 = dbl(dbl(dbl(t0)));
+  const F t0b = sub(t0, add(dbl(t2), t2));
+  // level 2: t2 z8, t1 z8, t0b (t0 + t2), t0b t3
+  a = t2; b = z8;
+  coop_pick(a, l == 1, t1);
+  coop_pick(a, l == 2, t0b); coop_pick(b, l == 2, add(t0, t2));
+  coop_pick(a, l == 3, t0b); coop_pick(b, l == 3, t3);
+  const F r2 = coop_product(a, b, g);
+  p.x = dbl(coop_bcast(r2, 3, g));
+  p.y = add(coop_bcast(r2, 0, g), coop_bcast(r2, 2, g));
+  p.z = coop_bcast(r2, 1, g);
+}
+template <class F>
+__device__ __noinline__ void coop_hadd(Hom<F>& acc, const Hom<F>& q, const CoopGroup g) {
+  const int l = g.lane;
+  // level 1: X1X2, Y1Y2, Z1Z2, (X1+Y1)(X2+Y2), (Y1+Z1)(Y2+Z2), (X1+Z1)(X2+Z2)
+  F a = acc.x, b = q.x;
+  coop_pick(a, l == 1, acc.y); coop_pick(b, l == 1, q.y);
+  coop_pick(a, l == 2, acc.z); coop_pick(b, l == 2, q.z);
+  coop_pick(a, l == 3, add(acc.x, acc.y)); coop_pick(b, l == 3, add(q.x, q.y));
+  coop_pick(a, l == 4, add(acc.y, acc.z)); coop_pick(b, l == 4, add(q.y, q.z));
+  coop_pick(a, l == 5, add(acc.x, acc.z)); coop_pick(b, l == 5, add(q.x, q.z));
+  const F r1 = coop_product(a, b, g);
+  F t0 = coop_bcast(r1, 0, g), t1 = coop_bcast(r1, 1, g), t2 = coop_bcast(r1, 2, g);
+  const F t3 = sub(sub(coop_bcast(r1, 3, g), t0), t1);
+  const F t4 = sub(sub(coop_bcast(r1, 4, g), t1), t2);
+  const F y3 = mul_b3(sub(sub(coop_bcast(r1, 5, g), t0), t2));
+  t0 = add(dbl(t0), t0);
+  t2 = mul_b3(t2);
+  const F z3 = add(t1, t2);
+  t1 = sub(t1, t2);
+  // level 2: t3 t1, t4 y3, t1 z3, y3 t0, z3 t4, t0 t3
+  a = t3; b = t1;
+  coop_pick(a, l == 1, t4); coop_pick(b, l == 1, y3);
+  coop_pick(a, l == 2, t1); coop_pick(b, l == 2, z3);
+  coop_pick(a, l == 3, y3); coop_pick(b, l == 3, t0);
+  coop_pick(a, l == 4, z3); coop_pick(b, l == 4, t4);
+  coop_pick(a, l == 5, t0); coop_pick(b, l == 5, t3);
+  const F r2 = coop_product(a, b, g);
+  acc.x = sub(coop_bcast(r2, 0, g), coop_bcast(r2, 1, g));
+  acc.y = add(coop_bcast(r2, 2, g), coop_bcast(r2, 3, g));
+  acc.z = add(coop_bcast(r2, 4, g), coop_bcast(r2, 5, g));
+}
+// conversions: one and two levels
+template <class F>
+__device__ __noinline__ Hom<F> coop_xyzz_to_hom(const XYZZ<F>& p, const CoopGroup g) {
+  if (is_inf(p)) return hom_inf<F>();      // uniform across the group
+  const int l = g.lane;
+  F a = p.x, b = p.zzz;
+  coop_pick(a, l == 1, p.y); coop_pick(b, l == 1, p.zz);
+  coop_pick(a, l == 2, p.zz);
+  const F r1 = coop_product(a, b, g);
+  Hom<F> r;
+  r.x = coop_bcast(r1, 0, g); r.y = coop_bcast(r1, 1, g); r.z = coop_bcast(r1, 2, g);
+  return r;
+}
+template <class F>
+__device__ __noinline__ XYZZ<F> coop_hom_to_xyzz(const Hom<F>& p, const CoopGroup g) {
+  const int l = g.lane;
+  F a = p.z, b = p.z;
+  coop_pick(a, l == 1, p.x);
+  const F r1 = coop_product(a, b, g);
+  XYZZ<F> r;
+  r.zz = coop_bcast(r1, 0, g); r.x = coop_bcast(r1, 1, g);
+  a = r.zz; b = p.z;
+  coop_pick(b, l == 1, p.y);
+  const F r2 = coop_product(a, b, g);
+  r.zzz = coop_bcast(r2, 0, g); r.y = coop_bcast(r2, 1, g);
+  return r;
+}
+
 #endif  // __CUDACC__
 }  // namespace b200

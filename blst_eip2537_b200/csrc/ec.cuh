@@ -169,6 +169,68 @@ B200_HD_NI void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
   acc.zzz = mul(mul(acc.zzz, q.zzz), ppp);
 }
 
+// ---- homogeneous projective coordinates with the COMPLETE formulas of Renes-Costello-Batina (a = 0) -------------------
+// x = X/Z, y = Y/Z, infinity = (0:1:0).  Used by the latency-bound tail of the MSM (window walk, window combine): both the
+// addition (Alg. 7: 12 products in TWO dependency levels) and the doubling (Alg. 9: 8 products in two levels) are
+// shallower than the XYZZ forms (4 and 3 levels), and they have no exceptional cases on E(Fp) and E'(Fp2), whose orders
+// are odd (the only exceptional pairs of the underlying Bosma-Lenstra law differ by a point of order two).
+template <class F>
+struct Hom { F x, y, z; };
+B200_HD Fp mul_b3(const Fp& t) {            // 3b = 12 on E: y^2 = x^3 + 4
+  const Fp t4 = dbl(dbl(t));
+  return add(dbl(t4), t4);
+}
+B200_HD Fp2 mul_b3(const Fp2& t) {          // 3b' = 12 (1 + u) on E': y^2 = x^3 + 4 (1 + u)
+  const Fp2 t4 = dbl(dbl(mul_xi(t)));
+  return add(dbl(t4), t4);
+}
+template <class F>
+B200_HD Hom<F> hom_inf() { Hom<F> r; r.x = FieldOps<F>::zero(); r.y = FieldOps<F>::one(); r.z = FieldOps<F>::zero(); return r; }
+template <class F>
+B200_HD_NI Hom<F> xyzz_to_hom(const XYZZ<F>& p) {      // X ZZZ : Y ZZ : ZZ ZZZ
+  if (is_inf(p)) return hom_inf<F>();
+  Hom<F> r;
+  r.x = mul(p.x, p.zzz); r.y = mul(p.y, p.zz); r.z = mul(p.zz, p.zzz);
+  return r;
+}
+template <class F>
+B200_HD_NI XYZZ<F> hom_to_xyzz(const Hom<F>& p) {      // X Z, Y Z^2, Z^2, Z^3
+  XYZZ<F> r;
+  r.zz = sqr(p.z);
+  r.zzz = mul(r.zz, p.z);
+  r.x = mul(p.x, p.z);
+  r.y = mul(p.y, r.zz);
+  return r;
+}
+template <class F>
+B200_HD_NI Hom<F> hom_dbl(const Hom<F>& p) {
+  const F t0 = sqr(p.y), t1 = mul(p.y, p.z), t3 = mul(p.x, p.y);
+  const F z8 = dbl(dbl(dbl(t0)));
+  const F t2 = mul_b3(sqr(p.z));
+  const F t0b = sub(t0, add(dbl(t2), t2));
+  Hom<F> r;
+  r.x = dbl(mul(t0b, t3));
+  r.y = add(mul(t2, z8), mul(t0b, add(t0, t2)));
+  r.z = mul(t1, z8);
+  return r;
+}
+template <class F>
+B200_HD_NI Hom<F> hom_add(const Hom<F>& p, const Hom<F>& q) {
+  F t0 = mul(p.x, q.x), t1 = mul(p.y, q.y), t2 = mul(p.z, q.z);
+  const F t3 = sub(sub(mul(add(p.x, p.y), add(q.x, q.y)), t0), t1);
+  const F t4 = sub(sub(mul(add(p.y, p.z), add(q.y, q.z)), t1), t2);
+  const F y3 = mul_b3(sub(sub(mul(add(p.x, p.z), add(q.x, q.z)), t0), t2));
+  t0 = add(dbl(t0), t0);
+  t2 = mul_b3(t2);
+  const F z3 = add(t1, t2);
+  t1 = sub(t1, t2);
+  Hom<F> r;
+  r.x = sub(mul(t3, t1), mul(t4, y3));
+  r.y = add(mul(t1, z3), mul(y3, t0));
+  r.z = add(mul(z3, t4), mul(t0, t3));
+  return r;
+}
+
 // x = X/ZZ, y = Y/ZZZ with one inversion; infinity -> (0,0)
 template <class F>
 B200_HD_NI Affine<F> xyzz_to_affine(const XYZZ<F>& p) {

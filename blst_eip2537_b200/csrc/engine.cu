@@ -513,7 +513,7 @@ static int msm_tail(Engine& e, MsmRun<F>& r, XYZZ<F>* d_partial, const unsigned 
     nodes_per_win = out_per_win;
     K = K_out;
   }
-  XYZZ<F>* tw = (XYZZ<F>*)((char*)e.nodes_b.ptr + node_words);      // T_w of every window, behind the node vectors
+  Hom<F>* tw = (Hom<F>*)((char*)e.nodes_b.ptr + node_words);        // T_w of every window, behind the node vectors
   LAUNCH(k_window_finish<F>, (unsigned)plan.nwin, 8 * Coop<F>::LANES, s, cur, K, lv, tw);
   g_stage.mark(3, s);
   LAUNCH(k_window_combine<F>, 1, 32, s, tw, plan, d_partial, d_status, d_status_copy);

@@ -508,20 +508,23 @@ __global__ void __launch_bounds__(128) k_reduce_level(const XYZZ<F>* __restrict_
   }
   out[(size_t)t * K_out + k] = acc;
 }
-// One block of 8 lane groups per window: groups form U_i = sum_t t*a_{i,t} in parallel, then group 0 walks
-// T = w + 2^cov_0 (U_0 + 2^(cov_1 - cov_0) (U_1 + ...)).
+// One block of 8 lane groups per window: the groups form U_i = sum_t t*a_{i,t} in parallel and convert them (and w) to
+// homogeneous coordinates, then group 0 walks T = w + 2^cov_0 (U_0 + 2^(cov_1 - cov_0) (U_1 + ...)) with the complete
+// two-level formulas of coop.cuh (coop_hadd / coop_hdbl).
 template <class F>
-__global__ void k_window_finish(const XYZZ<F>* __restrict__ roots, int K, ReduceLevels lv, XYZZ<F>* __restrict__ tw) {
-  __shared__ XYZZ<F> U[REDUCE_MAX_LEVELS];
+__global__ void k_window_finish(const XYZZ<F>* __restrict__ roots, int K, ReduceLevels lv, Hom<F>* __restrict__ tw) {
+  __shared__ Hom<F> U[REDUCE_MAX_LEVELS + 1];
   const CoopGroup g = coop_group<F>();
   const int grp = threadIdx.x / Coop<F>::LANES, ngrp = blockDim.x / Coop<F>::LANES;
   const XYZZ<F>* r = roots + (size_t)blockIdx.x * K;
   int base = 2;
-  for (int i = 0; i < lv.n; i++) {
-    const int L = 1 << lv.l_log[i];
+  for (int i = 0; i <= lv.n; i++) {
+    const int L = i < lv.n ? 1 << lv.l_log[i] : 0;
     if (i % ngrp == grp) {
       XYZZ<F> u;
-      if (L == 2) {
+      if (i == lv.n) {
+        u = r[1];                                 // sum of the leaf w's
+      } else if (L == 2) {
         u = r[base];
       } else if (L == 4) {                        // a1 + 2 a2 + 3 a3 = (a1 + a3) + 2 (a2 + a3)
         XYZZ<F> a3 = r[base + 2], y = r[base];
@@ -533,41 +536,43 @@ __global__ void k_window_finish(const XYZZ<F>* __restrict__ roots, int K, Reduce
         u = xyzz_inf<F>();
         for (int t = L - 1; t >= 1; t--) { XYZZ<F> a = r[base + t - 1]; coop_add(run, a, g); coop_add(u, run, g); }
       }
-      if (g.lane == 0 && g.sub == 0) U[i] = u;
+      const Hom<F> h = coop_xyzz_to_hom(u, g);
+      if (g.lane == 0 && g.sub == 0) U[i] = h;
     }
     base += L - 1;
   }
   __syncthreads();
   if (grp != 0) return;
-  XYZZ<F> acc = xyzz_inf<F>();
+  Hom<F> acc = hom_inf<F>();
   for (int i = lv.n - 1; i >= 0; i--) {
-    XYZZ<F> u = U[i];
-    coop_add(acc, u, g);
+    const Hom<F> u = U[i];
+    coop_hadd(acc, u, g);
     const int nd = lv.cov[i] - (i > 0 ? lv.cov[i - 1] : 0);
-    for (int k = 0; k < nd; k++) coop_dbl(acc, g);
+    for (int k = 0; k < nd; k++) coop_hdbl(acc, g);
   }
-  XYZZ<F> w = r[1];
-  coop_add(acc, w, g);
+  const Hom<F> w = U[lv.n];
+  coop_hadd(acc, w, g);
   if (g.lane == 0 && g.sub == 0) tw[blockIdx.x] = acc;
 }
 
-// Horner over the windows from the top down: acc = 2^width[w] * acc + T_w.
-// One cooperative lane group walks the ~240 sequential doublings.
+// Horner over the windows from the top down: acc = 2^width[w] * acc + T_w, in homogeneous coordinates (two dependency
+// levels per doubling instead of XYZZ's three).  One cooperative lane group walks the ~240 sequential doublings.
 // The result (and, when asked, a copy of the shard's first-error key) may be written through a PEER pointer into
 // another GPU's gather buffer: the multi-GPU exchange is fused into this last kernel of the shard's pipeline.
 template <class F>
-__global__ void k_window_combine(const XYZZ<F>* __restrict__ tw, MsmPlan plan, XYZZ<F>* __restrict__ acc_io,
+__global__ void k_window_combine(const Hom<F>* __restrict__ tw, MsmPlan plan, XYZZ<F>* __restrict__ acc_io,
                                  const unsigned long long* __restrict__ status_src, unsigned long long* __restrict__ status_dst) {
   if (blockIdx.x != 0 || threadIdx.x >= Coop<F>::LANES) return;
   if (threadIdx.x == 0 && status_dst) *status_dst = *status_src;
   const CoopGroup g = coop_group<F>();
-  XYZZ<F> acc = xyzz_inf<F>();
-  for (int w = plan.nwin - 1; w >= 0; w--) {
-    for (int k = 0; k < plan.width[w]; k++) coop_dbl(acc, g);   // acc is still infinity for the top window
-    XYZZ<F> t = tw[w];
-    coop_add(acc, t, g);
+  Hom<F> acc = tw[plan.nwin - 1];
+  for (int w = plan.nwin - 2; w >= 0; w--) {
+    for (int k = 0; k < plan.width[w]; k++) coop_hdbl(acc, g);
+    const Hom<F> t = tw[w];
+    coop_hadd(acc, t, g);
   }
-  if (g.lane == 0 && g.sub == 0) *acc_io = acc;
+  const XYZZ<F> out = coop_hom_to_xyzz(acc, g);
+  if (g.lane == 0 && g.sub == 0) *acc_io = out;
 }
 
 // sum `count` partial results (multi-GPU gather, or count = 1), convert to affine, encode

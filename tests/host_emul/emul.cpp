@@ -133,9 +133,10 @@ static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, 
     delete[] vec; vec = nxt; npw = opw; K = K_out;
   }
   if (K != reduce_root_width(lv) || npw != 1) { delete[] vec; delete[] cur; delete[] buckets; return -100; }
+  Hom<F>* tw = new Hom<F>[plan.nwin];
   for (int win = 0; win < plan.nwin; win++) {
     const XYZZ<F>* r = vec + (size_t)win * K;
-    XYZZ<F> tacc = xyzz_inf<F>();
+    Hom<F> tacc = hom_inf<F>();
     int base = 2;
     XYZZ<F> U[REDUCE_MAX_LEVELS];
     for (int i = 0; i < lv.n; i++) {
@@ -145,19 +146,20 @@ static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, 
       U[i] = u; base += L - 1;
     }
     for (int i = lv.n - 1; i >= 0; i--) {
-      xyzz_add(tacc, U[i]);
+      tacc = hom_add(tacc, xyzz_to_hom(U[i]));
       const int nd = lv.cov[i] - (i > 0 ? lv.cov[i - 1] : 0);
-      for (int q = 0; q < nd; q++) tacc = xyzz_dbl(tacc);
+      for (int q = 0; q < nd; q++) tacc = hom_dbl(tacc);
     }
-    xyzz_add(tacc, r[1]);
-    cur[win].w = tacc;
+    tw[win] = hom_add(tacc, xyzz_to_hom(r[1]));
   }
   delete[] vec;
-  XYZZ<F> acc = xyzz_inf<F>();
+  Hom<F> hacc = hom_inf<F>();
   for (int win = plan.nwin - 1; win >= 0; win--) {
-    for (int q = 0; q < plan.width[win]; q++) acc = xyzz_dbl(acc);
-    xyzz_add(acc, cur[win].w);
+    for (int q = 0; q < plan.width[win]; q++) hacc = hom_dbl(hacc);
+    hacc = hom_add(hacc, tw[win]);
   }
+  delete[] tw;
+  XYZZ<F> acc = hom_to_xyzz(hacc);
   Affine<F> a = xyzz_to_affine(acc);
   uint32_t w[PW];
   encode_point(w, a);
@@ -165,7 +167,39 @@ static int msm_pippenger(unsigned char* out, const unsigned char* in, size_t n, 
   delete[] cur; delete[] buckets;
   return 0;
 }
+// Homogeneous complete formulas (ec.cuh Hom) against the XYZZ ones: P + Q, 2P, and every case the XYZZ code branches on.
+// in = two encoded points (curve points, any subgroup); returns a bit mask of mismatches.
+template <class F>
+static int hom_check(const unsigned char* in) {
+  const int PW = Wire<F>::POINT_WORDS;
+  uint32_t w[2 * 64];
+  load_words(w, in, 2 * PW);
+  Affine<F> p, q;
+  if (decode_point(p, w) || decode_point(q, w + PW)) return -1;
+  auto aff_eq = [](const Affine<F>& a, const Affine<F>& b) { return eq(a.x, b.x) && eq(a.y, b.y); };
+  auto H = [](const Affine<F>& a) { return xyzz_to_hom(xyzz_from_affine(a)); };
+  auto A = [](const Hom<F>& h) { return xyzz_to_affine(hom_to_xyzz(h)); };
+  int bad = 0;
+  XYZZ<F> s = xyzz_from_affine(p);
+  xyzz_add(s, xyzz_from_affine(q));
+  if (!aff_eq(xyzz_to_affine(s), A(hom_add(H(p), H(q))))) bad |= 1;
+  XYZZ<F> d = xyzz_from_affine(p);
+  xyzz_add(d, xyzz_from_affine(p));
+  if (!aff_eq(xyzz_to_affine(d), A(hom_dbl(H(p))))) bad |= 2;
+  if (!aff_eq(xyzz_to_affine(d), A(hom_add(H(p), H(p))))) bad |= 4;                       // addition law on equal points
+  const Affine<F> inf = xyzz_to_affine(xyzz_inf<F>());
+  if (!aff_eq(inf, A(hom_add(H(p), H(affine_neg(p)))))) bad |= 8;                          // opposite points
+  if (!aff_eq(p, A(hom_add(hom_inf<F>(), H(p)))) || !aff_eq(p, A(hom_add(H(p), hom_inf<F>())))) bad |= 16;
+  if (!aff_eq(inf, A(hom_add(hom_inf<F>(), hom_inf<F>()))) || !aff_eq(inf, A(hom_dbl(hom_inf<F>())))) bad |= 32;
+  // a non-trivial projective representative: 2P + Q with 2P kept projective on both sides
+  XYZZ<F> e = d;
+  xyzz_add(e, xyzz_from_affine(q));
+  if (!aff_eq(xyzz_to_affine(e), A(hom_add(xyzz_to_hom(d), H(q))))) bad |= 64;
+  if (!aff_eq(xyzz_to_affine(xyzz_dbl(d)), A(hom_dbl(hom_dbl(H(p)))))) bad |= 128;
+  return bad;
+}
 extern "C" {
+int emul_hom_check(int group, const unsigned char* in) { return group == 1 ? hom_check<Fp>(in) : hom_check<Fp2>(in); }
 int emul_g1_pippenger(unsigned char* out, const unsigned char* in, size_t n, int c) { return msm_pippenger<Fp>(out, in, n, c); }
 int emul_g2_pippenger(unsigned char* out, const unsigned char* in, size_t n, int c) { return msm_pippenger<Fp2>(out, in, n, c); }
 

@@ -179,6 +179,27 @@ def test_deferred_g2_membership_agrees_with_the_ladder(emul, oracle_c):
     print("exact ladder: %d Fp-mul, deferred comparison: %d, return codes seen: %s" % (c[0], c[1], sorted(seen)))
 
 
+def test_homogeneous_complete_formulas_equal_xyzz(emul, oracle_c):
+    """ec.cuh Hom (Renes-Costello-Batina complete addition / doubling, a = 0, used by the MSM tail) gives the same affine
+    points as the XYZZ formulas: P + Q, 2P, P + P through the addition law, P + (-P), infinity on either side, and
+    non-trivial projective representatives -- on subgroup members and on curve points outside the subgroups."""
+    rnd = random.Random(0x2537 + 44)
+    g1 = [oracle_c.g1_gen_mul(rnd.randrange(1, o.R)) for _ in range(4)]
+    g2 = [oracle_c.g2_gen_mul(rnd.randrange(1, o.R)) for _ in range(4)]
+    # curve points outside the r-torsion subgroup (MULTIEXP inputs are not subgroup-checked)
+    def off_g1():
+        while True:
+            x = rnd.randrange(o.P)
+            y = o.fp_sqrt((x * x * x + 4) % o.P)
+            if y is not None:
+                return o.encode_g1((x, y))
+    g1 += [off_g1() for _ in range(4)]
+    for i in range(len(g1)):
+        assert emul.emul_hom_check(1, g1[i] + g1[(i + 3) % len(g1)]) == 0
+    for i in range(len(g2)):
+        assert emul.emul_hom_check(2, g2[i] + g2[(i + 1) % len(g2)]) == 0
+
+
 def test_coop12_operation_tables(emul):
     """The warp-cooperative Fp12 operation tables (coop12.cuh), executed sequentially, equal the thread-level functions."""
     rnd = random.Random(12)
