@@ -60,13 +60,23 @@ __device__ __forceinline__ void coop_pick(F& dst, bool take, const F& v) {
   for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = take ? s[i] : d[i];
 }
 // the slot's product a*b, available in every lane of the slot
-__device__ __forceinline__ Fp coop_product(const Fp& a, const Fp& b, const CoopGroup&) { return mul(a, b); }
+// The cooperative kernels are latency-bound on a handful of warps, so their multiplication is the fully unrolled CIOS form
+// (1.34 us per dependent multiplication on a lone warp against 1.60 us rolled, profiles/r02_k1_probes.md); the code size
+// that stops the throughput kernels from using it does not matter in these small kernels.
+__device__ __forceinline__ Fp coop_mul(const Fp& a, const Fp& b) {
+#ifdef __CUDA_ARCH__
+  return mul_unrolled<12>(a, b);
+#else
+  return mul(a, b);
+#endif
+}
+__device__ __forceinline__ Fp coop_product(const Fp& a, const Fp& b, const CoopGroup&) { return coop_mul(a, b); }
 __device__ __forceinline__ Fp2 coop_product(const Fp2& a, const Fp2& b, const CoopGroup& g) {
   // sub-lane 0: a0*b0, 1: a1*b1, 2 (and the spare 3): (a0+a1)*(b0+b1)
   Fp x = add(a.c0, a.c1), y = add(b.c0, b.c1);
   coop_pick(x, g.sub == 0, a.c0); coop_pick(y, g.sub == 0, b.c0);
   coop_pick(x, g.sub == 1, a.c1); coop_pick(y, g.sub == 1, b.c1);
-  Fp t = mul(x, y);
+  Fp t = coop_mul(x, y);
   const int slot0 = g.base + g.lane * 4;
   Fp t0, t1, t2;
 #pragma unroll
