@@ -23,6 +23,7 @@
 #include "pairing.cuh"
 #include "coop12.cuh"
 #include "pairing_dot.cuh"
+#include "pairing_coop.cuh"
 #include "map.cuh"
 #include "../../include/eip2537_b200.h"
 
@@ -1334,7 +1335,12 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   g_pstage.mark(0, s);
   const bool small_batch = (long)n_calls <= g_pairing_coop_max.load();
   const bool dot_path = use_dot && !small_batch;
-  if (small_batch) {
+  // few pairs in all: decode, both membership tests and the line functions of a pair by lane groups (pairing_coop.cuh)
+  static const long pair_coop_max = getenv("B200_PAIR_COOP_MAX") ? atol(getenv("B200_PAIR_COOP_MAX")) : 2048;
+  const bool pair_coop = small_batch && (long)total_pairs <= pair_coop_max;
+  if (pair_coop) {
+    if (total_pairs) LAUNCH(k_pairing_pair_coop, (unsigned)total_pairs, 64, s, d_raw, total_pairs, lines, skip, pstat);
+  } else if (small_batch) {
     LAUNCH(k_pairing_decode_split, blocks_for(total_pairs, 32), 64, s, d_raw, total_pairs, g1, g2, pstat);
   } else if (dot_path) {     // G2 membership is decided by the line kernel (its walk of [|z|]Q is that test's ladder)
     LAUNCH(k_pairing_decode<false>, blocks_for(total_pairs, 64), 64, s, d_raw, total_pairs, g1, g2, pstat);
@@ -1351,13 +1357,13 @@ static int pairing_batch_device_impl(Engine& e, const uint32_t* d_raw, const uns
   //   (more than ~12 pairs per call) accumulate per chunk in parallel first and give the warp only the product of
   //   the chunk values and the final exponentiation.
   if (small_batch && total_pairs <= 12 * n_calls) {
-    LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
+    if (!pair_coop) LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
     g_pstage.mark(2, s);
     LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs, (uint32_t)1);
     g_pstage.mark(3, s);
     LAUNCH(k_pairing_call_coop, (unsigned)n_calls, 32, s, n_calls, d_offsets, lines, skip, total_pairs, d_outs, d_errs);
   } else if (!use_dot || small_batch) {
-    LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
+    if (!pair_coop) LAUNCH(k_pairing_lines, blocks_for(total_pairs, 64), 64, s, g1, g2, pstat, total_pairs, lines, skip);
     g_pstage.mark(2, s);
     LAUNCH(k_pairing_count, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, pstat, plan_state, d_errs, (uint32_t)PAIRING_MAX_CHUNK_THREAD);
     LAUNCH(k_pairing_plan, blocks_for(n_calls, 128), 128, s, d_offsets, n_calls, d_errs, wave_thread, fc, (uint32_t)PAIRING_MAX_CHUNK_THREAD,
