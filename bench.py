@@ -588,7 +588,14 @@ def measure(ctx, workload, logn, calls, pairs, steps, warmup, window=0, cpu=True
                           "calls": sum(DOT_MAC["cyc"] * 316 + DOT_MAC["mul"] * (37 + c - 1) for c in nch)}
             extra["pairs_per_chunk"] = chunk
             peak_mac = ctx.measured_peak_mac()
-            if stage:
+            if stage and calls <= 128:
+                # small batches run the lane-cooperative latency kernels (pairing_coop.cuh, coop12.cuh): per-stage times only
+                avg = np.mean(np.asarray(stage), axis=0)
+                extra["stage_ms"] = {"decode_subgroup_lines": float(avg[0] + avg[1]), "miller_final_exp": float(avg[2] + avg[3])}
+                roofline = {"bound": "latency", "kernel": "k_pairing_call_coop", "achieved": None, "peak": peak_mac / 1e12, "unit": "TMAC32/s",
+                            "frac": None, "traffic": None, "peak_source": PEAK_SOURCE,
+                            "algorithmic": "small batch: dependent-multiplication latency, not a throughput kernel (profiles/r02_msm_tail.md)"}
+            elif stage:
                 avg = np.mean(np.asarray(stage), axis=0)
                 extra["stage_ms"] = {"decode_subgroup": float(avg[0]), "lines": float(avg[1]), "accumulate": float(avg[2]), "final_exp": float(avg[3])}
                 extra["stage_frac_of_peak"] = {k: fme[k] * FME_MAC32 / (float(avg[i]) * 1e-3) / peak_mac for i, k in enumerate(("decode", "lines", "accumulate", "calls"))}

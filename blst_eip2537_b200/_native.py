@@ -33,7 +33,7 @@ EXT_FUNCTIONS = [
     "bls12_b200_init", "bls12_b200_shutdown", "bls12_b200_last_error", "bls12_b200_launch_count",
     "bls12_b200_set_window", "bls12_pairing_batch", "bls12_g1multiexp_batch", "bls12_g2multiexp_batch", "bls12_b200_msm_device", "bls12_b200_msm_partial_device", "bls12_b200_msm_partial_host",
     "bls12_b200_msm_combine_device", "bls12_b200_pairing_batch_device", "bls12_b200_g1_generator_mul",
-    "bls12_b200_g2_generator_mul", "bls12_b200_fp_microbench", "bls12_b200_selftest", "bls12_b200_points_check", "bls12_b200_points_check_device", "bls12_b200_set_checked_msm", "bls12_b200_set_pairing_coop_max", "bls12_map_fp_to_g1_batch", "bls12_map_fp2_to_g2_batch", "bls12_b200_partial_bytes", "bls12_b200_set_profile", "bls12_b200_last_msm_profile", "bls12_b200_last_pairing_profile",
+    "bls12_b200_g2_generator_mul", "bls12_b200_fp_microbench", "bls12_b200_selftest", "bls12_b200_points_check", "bls12_b200_points_check_device", "bls12_b200_set_checked_msm", "bls12_b200_set_pairing_coop_max", "bls12_map_fp_to_g1_batch", "bls12_map_fp2_to_g2_batch", "bls12_b200_partial_bytes", "bls12_b200_set_profile", "bls12_b200_last_msm_profile", "bls12_b200_last_msm_work", "bls12_b200_last_pairing_profile",
     "bls12_b200_init_multi", "bls12_b200_multi_gpus", "bls12_b200_device_launch_count", "bls12_b200_comm_unique_id", "bls12_b200_comm_init",
     "bls12_b200_comm_destroy", "bls12_b200_msm_sharded_device", "bls12_b200_msm_sharded_host", "bls12_b200_last_pairing_chunk",
 ]
@@ -101,6 +101,8 @@ def lib() -> ctypes.CDLL:
     L.bls12_b200_set_profile.argtypes = [i32]
     L.bls12_b200_last_msm_profile.restype = i32
     L.bls12_b200_last_msm_profile.argtypes = [vp, vp]
+    L.bls12_b200_last_msm_work.restype = i32
+    L.bls12_b200_last_msm_work.argtypes = [vp]
     L.bls12_b200_partial_bytes.restype = sz
     L.bls12_b200_partial_bytes.argtypes = [i32]
     L.bls12_b200_last_pairing_profile.restype = i32

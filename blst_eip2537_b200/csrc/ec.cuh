@@ -169,6 +169,41 @@ B200_HD_NI void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
   acc.zzz = mul(mul(acc.zzz, q.zzz), ppp);
 }
 
+// ---- affine + affine with a SHARED inversion (batched-affine bucket accumulation, msm.cuh k_pair_round) ------------------
+// The sum of two affine points costs one inversion, and inversions can be shared (Montgomery's trick): with the inverse of
+// the denominator handed in, an addition is 3 multiplications (lambda, lambda^2, y3) + 3 for the trick itself, against 10
+// for the XYZZ mixed addition.  pair_prepare classifies the pair and returns the denominator to be inverted (1 when none is
+// needed, so that the shared product never becomes zero); pair_finish completes it.  Inputs are adversarial (repeated
+// points, P / -P pairs, infinity): every case is exact.
+enum PairKind : int { PAIR_ADD = 0, PAIR_TAKE_A = 1, PAIR_TAKE_B = 2, PAIR_INF = 3, PAIR_DBL = 4 };
+template <class F>
+B200_HD int pair_prepare(const Affine<F>& a, const Affine<F>& b, F& den) {
+  den = FieldOps<F>::one();
+  if (is_inf(b)) return is_inf(a) ? PAIR_INF : PAIR_TAKE_A;
+  if (is_inf(a)) return PAIR_TAKE_B;
+  const F dx = sub(b.x, a.x);
+  if (is_zero(dx)) {
+    if (!eq(a.y, b.y)) return PAIR_INF;     // opposite points
+    den = dbl(a.y);                         // the same point: tangent (y != 0: the curves have odd order)
+    return PAIR_DBL;
+  }
+  den = dx;
+  return PAIR_ADD;
+}
+template <class F>
+B200_HD Affine<F> pair_finish(int kind, const Affine<F>& a, const Affine<F>& b, const F& inv_den) {
+  if (kind == PAIR_TAKE_A) return a;
+  if (kind == PAIR_TAKE_B) return b;
+  Affine<F> r;
+  if (kind == PAIR_INF) { r.x = FieldOps<F>::zero(); r.y = FieldOps<F>::zero(); return r; }
+  F num = sub(b.y, a.y);
+  if (kind == PAIR_DBL) { const F xx = sqr(a.x); num = add(dbl(xx), xx); }
+  const F lam = mul(num, inv_den);
+  r.x = sub(sub(sqr(lam), a.x), b.x);
+  r.y = sub(mul(lam, sub(a.x, r.x)), a.y);
+  return r;
+}
+
 // ---- homogeneous projective coordinates with the COMPLETE formulas of Renes-Costello-Batina (a = 0) -------------------
 // x = X/Z, y = Y/Z, infinity = (0:1:0).  Used by the latency-bound tail of the MSM (window walk, window combine): both the
 // addition (Alg. 7: 12 products in TWO dependency levels) and the doubling (Alg. 9: 8 products in two levels) are

@@ -139,6 +139,7 @@ struct Engine {
   cudaStream_t pending_stream = nullptr;
   // MSM workspaces
   Buffer raw, pts, digits, counts, offsets, block_sums, entries, buckets, nodes_a, nodes_b, partial, out, status, order, tasks, task_partials;
+  Buffer pair_a, pair_b, pair_layout;      // batched-affine pair rounds (msm.cuh k_pair_round)
   Buffer gather;                             // multi-GPU: N records of {partial sum, status key}
   // pairing workspaces
   Buffer pr_raw, pr_offsets, pr_lines, pr_tasks, pr_g1, pr_g2, pr_status, pr_f, pr_outs, pr_errs, pr_slots, pr_park, pr_prog;
@@ -147,7 +148,7 @@ struct Engine {
   unsigned long long* h_status = nullptr;    // pinned
   StageRing ring;
   std::vector<Buffer*> all_buffers() {
-    return {&raw, &pts, &digits, &counts, &offsets, &block_sums, &entries, &buckets, &nodes_a, &nodes_b, &partial, &out, &status,
+    return {&pair_a, &pair_b, &pair_layout, &raw, &pts, &digits, &counts, &offsets, &block_sums, &entries, &buckets, &nodes_a, &nodes_b, &partial, &out, &status,
             &order, &tasks, &task_partials, &gather, &pr_raw, &pr_offsets, &pr_lines, &pr_tasks, &pr_g1, &pr_g2, &pr_status, &pr_f,
             &pr_outs, &pr_errs, &pr_slots, &pr_park, &pr_prog};
   }
@@ -346,7 +347,25 @@ struct StageTimer {
 };
 static StageTimer g_stage;
 static StageTimer g_pstage;   // pairing: decode | lines | plan+accumulate | calls
-static unsigned long long g_last_entries = 0;
+static unsigned long long g_last_entries = 0, g_last_affine_adds = 0, g_last_walk_adds = 0;
+static const uint32_t* g_work_counts = nullptr; static size_t g_work_nbt = 0; static int g_work_rounds = 0, g_work_device = 0;
+// bucket sizes of the last profiled MULTIEXP -> D = non-zero digits, additions done pairwise in affine form, additions of the XYZZ walk
+// (read back from the workspace on request: valid until the next call on that workspace; developer / bench mode, one caller)
+static void msm_count_work() {
+  if (!g_work_counts) return;
+  std::vector<uint32_t> hc(g_work_nbt);
+  int prev = 0; cudaGetDevice(&prev); cudaSetDevice(g_work_device);
+  cudaMemcpy(hc.data(), g_work_counts, g_work_nbt * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  cudaSetDevice(prev);
+  unsigned long long D = 0, aff = 0, walk = 0;
+  for (uint32_t m : hc) {
+    D += m;
+    for (int k = 0; k < g_work_rounds; k++) { aff += m / 2; m = (m + 1) / 2; }
+    walk += m;
+  }
+  g_last_entries = D; g_last_affine_adds = aff; g_last_walk_adds = walk;
+  g_work_counts = nullptr;
+}
 
 // The MSM runs in three phases so that a host-resident input can be STREAMED: bucket accumulation is
 // additive, so each chunk of pairs is decoded, sorted and accumulated on top of the buckets left by
@@ -360,6 +379,8 @@ struct MsmRun {
   Affine<F>* pts; int* digits; uint32_t *counts, *cursors, *offsets, *block_sums, *entries, *order, *bin_total, *bin_start;
   OrderCounters* oc; OverflowTask* tasks; BigBucket* big; XYZZ<F>* task_partials; XYZZ<F>* buckets;
   size_t max_tasks;
+  int rounds;                                  // batched-affine pair rounds before the XYZZ walk (0 = none)
+  Affine<F>*pair_a, *pair_b; uint32_t *counts_r, *offsets_r, *total_padded;
 };
 
 template <class F>
@@ -383,7 +404,20 @@ static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
   if ((rc = e.counts.reserve(2 * nbt * sizeof(uint32_t)))) return rc;       // counts + cursors
   if ((rc = e.offsets.reserve(nbt * sizeof(uint32_t)))) return rc;
   if ((rc = e.block_sums.reserve((nbt / 1024 + 2) * sizeof(uint32_t)))) return rc;
-  if ((rc = e.entries.reserve(chunk_n * plan.nwin * sizeof(uint32_t)))) return rc;
+  // Batched-affine pair rounds (msm.cuh k_pair_round) are OPT-IN (B200_AFFINE_ROUNDS = 1 or 2): bit-exact, but measured at
+  // break-even on this pipeline (G1 2^20: accumulate stage 6.40 ms against 6.37 ms; profiles/r02_msm_tail.md).
+  {
+    static const int rounds_env = getenv("B200_AFFINE_ROUNDS") ? atoi(getenv("B200_AFFINE_ROUNDS")) : 0;
+    r.rounds = rounds_env < 0 ? 0 : (rounds_env > 2 ? 2 : rounds_env);
+  }
+  const size_t pad_slots = r.rounds ? nbt * (((size_t)1 << r.rounds) - 1) : 0;
+  if ((rc = e.entries.reserve((chunk_n * plan.nwin + pad_slots + 4) * sizeof(uint32_t)))) return rc;
+  if (r.rounds) {
+    const size_t bound = chunk_n * plan.nwin + pad_slots;
+    if ((rc = e.pair_a.reserve((bound / 2 + 1) * sizeof(Affine<F>)))) return rc;
+    if (r.rounds > 1 && (rc = e.pair_b.reserve((bound / 4 + 1) * sizeof(Affine<F>)))) return rc;
+    if ((rc = e.pair_layout.reserve((2 * nbt + 4) * sizeof(uint32_t)))) return rc;
+  }
   if ((rc = e.buckets.reserve(nbt * sizeof(XYZZ<F>)))) return rc;
   r.max_tasks = (chunk_n * (size_t)plan.nwin) / 64 + 2;      // cap >= 64 entries per task
   if ((rc = e.order.reserve(nbt * sizeof(uint32_t) + 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters)))) return rc;
@@ -404,6 +438,11 @@ static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
   r.tasks = (OverflowTask*)e.tasks.ptr;
   r.big = (BigBucket*)(r.tasks + r.max_tasks);
   r.task_partials = (XYZZ<F>*)e.task_partials.ptr;
+  r.pair_a = (Affine<F>*)e.pair_a.ptr;
+  r.pair_b = (Affine<F>*)e.pair_b.ptr;
+  r.counts_r = (uint32_t*)e.pair_layout.ptr;
+  r.offsets_r = r.counts_r ? r.counts_r + nbt : nullptr;
+  r.total_padded = r.counts_r ? r.offsets_r + nbt : nullptr;
   return E_SUCCESS;
 }
 
@@ -426,45 +465,60 @@ static int msm_feed(Engine& e, MsmRun<F>& r, const uint32_t* d_raw, size_t n, ui
   }
   LAUNCH(k_digits<F>, blocks_for(n, 256), 256, s, d_raw, n, r.pts, plan, r.digits, r.counts, glv);
   unsigned nblk = blocks_for(nbt, 1024);
-  LAUNCH(k_scan_blocks, nblk, 1024, s, r.counts, r.offsets, r.block_sums, (uint32_t)nbt);
+  const int R = r.rounds;
+  const uint32_t pad_mask = (1u << R) - 1;
+  const size_t total_digits = nv * plan.nwin;
+  const size_t entry_bound = total_digits + (R ? nbt * (size_t)pad_mask : 0);     // sorted entries incl. alignment padding
+  if (R) CUDA_TRY(cudaMemsetAsync(r.entries, 0xFF, entry_bound * sizeof(uint32_t), s));   // ENTRY_NONE in the padding slots
+  LAUNCH(k_scan_blocks, nblk, 1024, s, r.counts, r.offsets, r.block_sums, (uint32_t)nbt, pad_mask);
   LAUNCH(k_scan_sums, 1, 1024, s, r.block_sums, nblk);
   LAUNCH(k_scan_fix, nblk, 1024, s, r.offsets, r.block_sums, (uint32_t)nbt);
   LAUNCH(k_scatter, blocks_for(nv * plan.nwin, 256), 256, s, r.digits, nv, plan, r.offsets, r.cursors, r.entries);
+  if (first) g_stage.mark(1, s);     // stage "accumulate" = pair rounds + bucket schedule + XYZZ walk
+  // batched-affine pair rounds: the segments shrink 2^R-fold before the XYZZ walk
+  const Affine<F>* walk_pts = r.pts;
+  const uint32_t *walk_counts = r.counts, *walk_offsets = r.offsets;
+  if (R) {
+    LAUNCH(k_pair_total, 1, 1, s, r.counts, r.offsets, (uint32_t)nbt, R, r.total_padded);
+    LAUNCH((k_pair_round<F, true, PAIR_BATCH>), blocks_for(entry_bound / 2 + 1, 128 * PAIR_BATCH), 128, s, r.pts, r.entries, r.total_padded, 0, r.pair_a);
+    if (R > 1) LAUNCH((k_pair_round<F, false, PAIR_BATCH>), blocks_for(entry_bound / 4 + 1, 128 * PAIR_BATCH), 128, s, r.pair_a, (const uint32_t*)nullptr, r.total_padded, 1, r.pair_b);
+    LAUNCH(k_pair_layout, blocks_for(nbt, 256), 256, s, r.counts, r.offsets, (uint32_t)nbt, R, r.counts_r, r.offsets_r);
+    walk_pts = R > 1 ? r.pair_b : r.pair_a;
+    walk_counts = r.counts_r; walk_offsets = r.offsets_r;
+  }
   // size-ordered bucket schedule + overflow plan for oversized buckets
-  const size_t total_digits = nv * plan.nwin;
-  uint32_t cap = (uint32_t)(4 * (total_digits / nbt + 1) + 64);
+  uint32_t cap = (uint32_t)(4 * ((total_digits >> R) / nbt + 1) + 64);
   CUDA_TRY(cudaMemsetAsync(r.bin_total, 0, 2 * ORDER_BINS * sizeof(uint32_t) + sizeof(OrderCounters), s));
-  LAUNCH(k_order_hist, nblk, 1024, s, r.counts, r.offsets, (uint32_t)nbt, cap, r.bin_total, r.oc, r.big, r.tasks);
+  LAUNCH(k_order_hist, nblk, 1024, s, walk_counts, walk_offsets, (uint32_t)nbt, cap, r.bin_total, r.oc, r.big, r.tasks);
   LAUNCH(k_order_scan, 1, 1024, s, r.bin_total, r.bin_start);
-  LAUNCH(k_order_scatter, nblk, 1024, s, r.counts, (uint32_t)nbt, r.bin_start, r.order);
-  if (first) g_stage.mark(1, s);
+  LAUNCH(k_order_scatter, nblk, 1024, s, walk_counts, (uint32_t)nbt, r.bin_start, r.order);
   // multiply-loop unrolling in k_accumulate<Fp> (6 rows per iteration: -2.3 % on the kernel, profiles/r02_k1_probes.md) and the
   // register budget of k_accumulate<Fp2>; B200_ACC_ROWS / B200_ACC_G2_BLOCKS are developer switches
   static const int acc_rows = getenv("B200_ACC_ROWS") ? atoi(getenv("B200_ACC_ROWS")) : 6;
   static const int g2_blocks = getenv("B200_ACC_G2_BLOCKS") ? atoi(getenv("B200_ACC_G2_BLOCKS")) : 4;
   const unsigned acc_grid = blocks_for(nbt, 128);
   const int add_flag = first ? 0 : 1;
-  if (sizeof(F) == sizeof(Fp)) {
-    if (acc_rows == 6)       LAUNCH((k_accumulate<F, 6, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
-    else if (acc_rows == 12) LAUNCH((k_accumulate<F, 12, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
-    else                     LAUNCH((k_accumulate<F, 2, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+#define ACC_LAUNCH(K) LAUNCH(K, acc_grid, 128, s, walk_pts, r.entries, walk_offsets, walk_counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets)
+  if (R) {
+    if (sizeof(F) == sizeof(Fp)) ACC_LAUNCH((k_accumulate<F, 6, 4, true>));
+    else                         ACC_LAUNCH((k_accumulate<F, 2, 4, true>));
+  } else if (sizeof(F) == sizeof(Fp)) {
+    if (acc_rows == 6)       ACC_LAUNCH((k_accumulate<F, 6, 4>));
+    else if (acc_rows == 12) ACC_LAUNCH((k_accumulate<F, 12, 4>));
+    else                     ACC_LAUNCH((k_accumulate<F, 2, 4>));
   } else {
-    if (g2_blocks == 2)      LAUNCH((k_accumulate<F, 2, 2>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
-    else if (g2_blocks == 3) LAUNCH((k_accumulate<F, 2, 3>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
-    else                     LAUNCH((k_accumulate<F, 2, 4>), acc_grid, 128, s, r.pts, r.entries, r.offsets, r.counts, r.order, (uint32_t)nbt, cap, add_flag, r.buckets);
+    if (g2_blocks == 2)      ACC_LAUNCH((k_accumulate<F, 2, 2>));
+    else if (g2_blocks == 3) ACC_LAUNCH((k_accumulate<F, 2, 3>));
+    else                     ACC_LAUNCH((k_accumulate<F, 2, 4>));
   }
-  const size_t tasks_bound = total_digits / cap + 2;
-  LAUNCH(k_accumulate_overflow<F>, blocks_for(tasks_bound, 128), 128, s, r.pts, r.entries, r.tasks, r.oc, r.task_partials);
+#undef ACC_LAUNCH
+  const size_t tasks_bound = (total_digits >> R) / cap + 2;
+  if (R) LAUNCH((k_accumulate_overflow<F, true>), blocks_for(tasks_bound, 128), 128, s, walk_pts, r.entries, r.tasks, r.oc, r.task_partials);
+  else   LAUNCH((k_accumulate_overflow<F, false>), blocks_for(tasks_bound, 128), 128, s, walk_pts, r.entries, r.tasks, r.oc, r.task_partials);
   LAUNCH(k_merge_overflow<F>, blocks_for(tasks_bound * 32, 128), 128, s, r.big, r.oc, r.task_partials, r.buckets);
   if (first) {
     g_stage.mark(2, s);
-    if (g_profile.load()) {   // total sorted entries = non-zero digits D (algorithmic work of k_accumulate)
-      uint32_t last_off = 0, last_cnt = 0;
-      cudaMemcpyAsync(&last_off, r.offsets + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
-      cudaMemcpyAsync(&last_cnt, r.counts + nbt - 1, 4, cudaMemcpyDeviceToHost, s);
-      cudaStreamSynchronize(s);
-      g_last_entries = (unsigned long long)last_off + last_cnt;
-    }
+    if (g_profile.load()) { g_work_counts = r.counts; g_work_nbt = nbt; g_work_rounds = R; g_work_device = e.device; }   // counted lazily (bls12_b200_last_msm_work)
   }
   CUDA_TRY(cudaGetLastError());
   return E_SUCCESS;
@@ -1889,6 +1943,13 @@ extern "C" EIP2537_ERROR bls12_b200_last_msm_profile(float* stage_ms4, uint64_t*
   if (g_stage.used < 5) return EIP2537_EMPTY_INPUT;
   CUDA_TRY2(cudaEventSynchronize(g_stage.ev[4]));
   for (int i = 0; i < 4; i++) CUDA_TRY2(cudaEventElapsedTime(&stage_ms4[i], g_stage.ev[i], g_stage.ev[i + 1]));
+  msm_count_work();
   *nonzero_digits = g_last_entries;
+  return EIP2537_SUCCESS;
+}
+// work3 = {non-zero digits D, additions done pairwise in affine form (6 Fp-mul each), additions of the XYZZ walk (10 / 28 Fp-mul)}
+extern "C" EIP2537_ERROR bls12_b200_last_msm_work(uint64_t* work3) {
+  msm_count_work();
+  work3[0] = g_last_entries; work3[1] = g_last_affine_adds; work3[2] = g_last_walk_adds;
   return EIP2537_SUCCESS;
 }

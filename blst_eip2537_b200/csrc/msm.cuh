@@ -232,11 +232,12 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ raw
 
 // ------------------------------------------------------------------------------------------ scan
 // three-kernel exclusive scan over m counters (m <= ~2^21): block-local scan, scan of block sums, fix-up
+// (pad_mask = 2^R - 1 rounds every count up to a multiple of 2^R: segments aligned for R rounds of pairwise additions)
 __global__ void __launch_bounds__(1024) k_scan_blocks(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                      uint32_t* __restrict__ block_sums, uint32_t m) {
+                                                      uint32_t* __restrict__ block_sums, uint32_t m, uint32_t pad_mask) {
   __shared__ uint32_t warp_sums[32];
   uint32_t i = blockIdx.x * 1024u + threadIdx.x;
-  uint32_t v = i < m ? in[i] : 0, x = v;
+  uint32_t v = i < m ? ((in[i] + pad_mask) & ~pad_mask) : 0, x = v;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -387,21 +388,129 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
   return r;
 }
 
-template <class F, int ROWS = 2>
+// DIRECT: the segment is a run of affine partial sums (output of the pair rounds; (0,0) = infinity) instead of entries
+template <class F, int ROWS = 2, bool DIRECT = false>
 __device__ __forceinline__ void accumulate_segment(XYZZ<F>& acc, const Affine<F>* __restrict__ pts,
                                                    const uint32_t* __restrict__ entries, uint32_t start, uint32_t cnt) {
   for (uint32_t k = 0; k < cnt; k++) {
-    uint32_t e = __ldg(entries + start + k);
-    Affine<F> pt = load_affine(pts + (e & 0x7fffffffu));
-    if (e >> 31) pt.y = neg(pt.y);
+    Affine<F> pt;
+    if constexpr (DIRECT) {
+      pt = load_affine(pts + start + k);
+      if (is_inf(pt)) continue;
+    } else {
+      uint32_t e = __ldg(entries + start + k);
+      pt = load_affine(pts + (e & 0x7fffffffu));
+      if (e >> 31) pt.y = neg(pt.y);
+    }
     if constexpr (ROWS != 2 && sizeof(F) == sizeof(Fp)) xyzz_madd_unrolled<ROWS>(acc, pt);
     else xyzz_madd(acc, pt);
   }
 }
 
+// ---- batched-affine pair rounds (opt-in: B200_AFFINE_ROUNDS) --------------------------------------------------------------
+// With segment offsets aligned to 2^R (k_scan_blocks pad_mask) and the padding slots holding ENTRY_NONE, the entries of a
+// bucket can be summed PAIRWISE before the sequential XYZZ walk: round 1 adds entries (2q, 2q+1) -> affine partial sum q,
+// round 2 adds partial sums (2q, 2q+1); a pair never straddles a bucket boundary, and bucket b's segment after R rounds is
+// [offsets[b] >> R, +padded_count >> R).  Each thread owns PAIR_BATCH output slots and the 32 lanes of a warp share ONE
+// inversion (ec.cuh pair_prepare / pair_finish: ~7 multiplications per addition, the trick included, instead of the 10 of the
+// mixed XYZZ addition).  Measured (G1 2^20, profiles/r02_msm_tail.md): the round runs at 65 % of the multiply pipe
+// (two random 96-byte gathers per addition in each of its two passes) and the stage ends at break-even, so the default
+// pipeline does not use it.
+static constexpr uint32_t ENTRY_NONE = 0xFFFFFFFFu;
+static constexpr int PAIR_BATCH = 64;       // output slots per thread: 2048 additions share one inversion per warp
+template <class F>
+__device__ __forceinline__ Affine<F> affine_inf() { Affine<F> r; r.x = FieldOps<F>::zero(); r.y = FieldOps<F>::zero(); return r; }
+template <class F, bool FIRST>
+__device__ __forceinline__ void pair_load(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries, uint32_t q,
+                                          Affine<F>& a, Affine<F>& b) {
+  if constexpr (FIRST) {
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(entries) + q);
+    a = affine_inf<F>(); b = affine_inf<F>();
+    if (e.x != ENTRY_NONE) { a = load_affine(src + (e.x & 0x7fffffffu)); if (e.x >> 31) a.y = neg(a.y); }
+    if (e.y != ENTRY_NONE) { b = load_affine(src + (e.y & 0x7fffffffu)); if (e.y >> 31) b.y = neg(b.y); }
+  } else {
+    a = load_affine(src + 2 * (size_t)q);
+    b = load_affine(src + 2 * (size_t)q + 1);
+  }
+}
+// total_padded = sorted entries incl. alignment padding (device scalar); this round reads total_padded >> shift slots.
+// ONE inversion per WARP: the 32 lanes' products are multiplied up a butterfly (every lane keeps the partner products it
+// met: they are exactly the other lanes' contribution), all lanes invert the same total (no divergence), and each lane
+// recovers its own inverse with five more multiplications.
+template <class F>
+__device__ __forceinline__ F shfl_xor_field(const F& v, int mask) {
+  F r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_xor_sync(0xffffffffu, s[i], mask);
+  return r;
+}
+template <class F, bool FIRST, int BATCH>
+__global__ void __launch_bounds__(128) k_pair_round(const Affine<F>* __restrict__ src, const uint32_t* __restrict__ entries,
+                                                    const uint32_t* __restrict__ total_padded, int shift, Affine<F>* __restrict__ out) {
+  const uint32_t n_out = (*total_padded >> shift) >> 1;
+  const uint32_t base = blockIdx.x * (128u * BATCH) + threadIdx.x;
+  if (base - (threadIdx.x & 31u) >= n_out) return;          // the whole warp is past the end
+  F pre[BATCH];
+  F run = FieldOps<F>::one();
+#pragma unroll 1
+  for (int i = 0; i < BATCH; i++) {
+    const uint32_t q = base + (uint32_t)i * 128u;
+    pre[i] = run;
+    if (q < n_out) {
+      Affine<F> a, b;
+      pair_load<F, FIRST>(src, entries, q, a, b);
+      F den;
+      pair_prepare(a, b, den);
+      run = mul(run, den);
+    }
+  }
+  F inv_run;
+  {
+    F other[5];
+    F cur = run;
+#pragma unroll
+    for (int k = 0; k < 5; k++) { other[k] = shfl_xor_field(cur, 1 << k); cur = mul(cur, other[k]); }
+    inv_run = inv(cur);                                      // the same value on all 32 lanes
+#pragma unroll
+    for (int k = 0; k < 5; k++) inv_run = mul(inv_run, other[k]);
+  }
+#pragma unroll 1
+  for (int i = BATCH - 1; i >= 0; i--) {
+    const uint32_t q = base + (uint32_t)i * 128u;
+    if (q >= n_out) continue;
+    Affine<F> a, b;
+    pair_load<F, FIRST>(src, entries, q, a, b);
+    F den;
+    const int kind = pair_prepare(a, b, den);
+    const F inv_den = mul(inv_run, pre[i]);
+    inv_run = mul(inv_run, den);
+    const Affine<F> r = pair_finish(kind, a, b, inv_den);
+    uint4* d = reinterpret_cast<uint4*>(out + q);
+    const uint4* sv = reinterpret_cast<const uint4*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(Affine<F>) / 16); k++) d[k] = sv[k];
+  }
+}
+// counts / offsets of the segments after R rounds, and the padded total (one thread per bucket)
+__global__ void __launch_bounds__(256) k_pair_layout(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t nbt,
+                                                     int R, uint32_t* __restrict__ counts_r, uint32_t* __restrict__ offsets_r) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbt) return;
+  const uint32_t mask = (1u << R) - 1;
+  counts_r[b] = (counts[b] + mask) >> R;
+  offsets_r[b] = offsets[b] >> R;
+}
+__global__ void k_pair_total(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t nbt, int R,
+                             uint32_t* __restrict__ total_padded) {
+  const uint32_t mask = (1u << R) - 1;
+  *total_padded = offsets[nbt - 1] + ((counts[nbt - 1] + mask) & ~mask);
+}
+
 // one thread per bucket, buckets taken in order of decreasing size; at most `cap` entries each
 // MINB: resident blocks per SM the register budget is sized for (4 -> 128 registers, 3 -> 168, 2 -> 255)
-template <class F, int ROWS = 2, int MINB = 4>
+template <class F, int ROWS = 2, int MINB = 4, bool DIRECT = false>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                     const uint32_t* __restrict__ order, uint32_t nbuckets_total, uint32_t cap,
@@ -413,11 +522,11 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F>* __res
   if (add_to_existing && cnt == 0) return;   // streamed chunks: the bucket keeps what earlier chunks left
   XYZZ<F> acc;
   if (add_to_existing) acc = buckets[b]; else acc = xyzz_inf<F>();
-  accumulate_segment<F, ROWS>(acc, pts, entries, offsets[b], cnt < cap ? cnt : cap);
+  accumulate_segment<F, ROWS, DIRECT>(acc, pts, entries, offsets[b], cnt < cap ? cnt : cap);
   buckets[b] = acc;
 }
 // one thread per overflow task
-template <class F>
+template <class F, bool DIRECT = false>
 __global__ void __launch_bounds__(128) k_accumulate_overflow(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                              const OverflowTask* __restrict__ tasks, const OrderCounters* __restrict__ oc,
                                                              XYZZ<F>* __restrict__ partials) {
@@ -425,7 +534,7 @@ __global__ void __launch_bounds__(128) k_accumulate_overflow(const Affine<F>* __
   if (t >= oc->ntasks) return;
   OverflowTask task = tasks[t];
   XYZZ<F> acc = xyzz_inf<F>();
-  accumulate_segment(acc, pts, entries, task.start, task.len);
+  accumulate_segment<F, 2, DIRECT>(acc, pts, entries, task.start, task.len);
   partials[t] = acc;
 }
 // one warp per oversized bucket: lanes sum strided subsets of its partials, then a shuffle tree

@@ -156,6 +156,9 @@ EIP2537_ERROR bls12_b200_fp_microbench(int mode, size_t n_threads, int iters, fl
  *      and the number of non-zero signed digits (= point additions done by the accumulate kernel) */
 void bls12_b200_set_profile(int on);
 EIP2537_ERROR bls12_b200_last_msm_profile(float* stage_ms4, uint64_t* nonzero_digits);
+/* work3 = { non-zero digits D of the last profiled MULTIEXP, bucket additions done pairwise in affine form with a shared
+ * inversion (6 field multiplications each), bucket additions done by the XYZZ walk (10, G2: 28) }.  bench.py's roofline. */
+EIP2537_ERROR bls12_b200_last_msm_work(uint64_t* work3);
 /* same for the pairing batch: stage_ms4 = {decode + subgroup checks, line functions,
  * chunked multi-Miller accumulate, Fp12 product + final exponentiation} */
 EIP2537_ERROR bls12_b200_last_pairing_profile(float* stage_ms4);

@@ -196,6 +196,12 @@ static int hom_check(const unsigned char* in) {
   xyzz_add(e, xyzz_from_affine(q));
   if (!aff_eq(xyzz_to_affine(e), A(hom_add(xyzz_to_hom(d), H(q))))) bad |= 64;
   if (!aff_eq(xyzz_to_affine(xyzz_dbl(d)), A(hom_dbl(hom_dbl(H(p)))))) bad |= 128;
+  // affine + affine with the inverse handed in (ec.cuh pair_prepare / pair_finish), every case k_pair_round can meet
+  auto P = [](const Affine<F>& a, const Affine<F>& b) { F den; const int kind = pair_prepare(a, b, den); return pair_finish(kind, a, b, inv(den)); };
+  if (!aff_eq(xyzz_to_affine(s), P(p, q))) bad |= 256;
+  if (!aff_eq(xyzz_to_affine(d), P(p, p))) bad |= 512;
+  if (!aff_eq(inf, P(p, affine_neg(p)))) bad |= 1024;
+  if (!aff_eq(p, P(inf, p)) || !aff_eq(p, P(p, inf)) || !aff_eq(inf, P(inf, inf))) bad |= 2048;
   return bad;
 }
 extern "C" {

@@ -8,6 +8,7 @@
 """
 import ctypes
 import os
+import random
 import sys
 import threading
 
@@ -189,6 +190,99 @@ def test_deferred_g2_membership_keeps_codes_and_precedence(product, oracle_c):
         assert bytes(outs[j]) == (ref if code == 0 else bytes(32)), j
         seen.add(code)
     assert seen == {0, 1, 2}
+
+
+def _adversarial_pairing_calls():
+    q_out = _g2_outside_subgroup()
+    small = _g2_small_order_points()
+    order3 = po.encode_g1((0, 2))
+    off1 = G1B[:64] + po.fp_to_bytes(5)
+    bad_field = bytes(16) + b"\xff" * 48 + G1B[64:]
+    rng = wl.SplitMix64(0x2537 + 62)
+    good = lambda k, truth=True: wl.pairing_call(k, rng, truth)
+    calls = [
+        good(1), good(2), good(2, False), good(5), good(16, False),
+        G1B + q_out + off1 + G2B,                       # G2 fault at pair 0 precedes the G1 fault at pair 1 -> 2
+        off1 + G2B + G1B + q_out,                       # the G1 fault comes first -> 1
+        G1B + G2B + bytes(128) + q_out,                 # infinite G1, Q outside G2 -> 2 (Q is still checked)
+        G1B + G2B + G1B + bytes(256),                   # infinite G2 is a member
+        bytes(128) + bytes(256),                        # both infinite
+        order3 + q_out,                                 # G1 membership is checked before G2
+        order3 + G2B,
+        bad_field + G2B,                                # field element >= p -> 3
+        good(3)[:384 * 2] + G1B + q_out,                # fault in the last pair
+    ]
+    for sp in small:
+        calls += [G1B + sp, G1B + G2B + G1B + sp + G1B + G2B, bytes(128) + sp]
+    return calls
+
+
+def test_small_batch_pairing_lane_group_and_thread_paths(product, oracle_c):
+    """Single calls and small batches walk each pair with lane groups (pairing_coop.cuh: complete homogeneous ladder for
+    the G1 test, cooperative line steps with the deferred G2 test); B200_PAIR_COOP_MAX=-1 in a fresh process keeps the
+    thread-per-pair kernels.  Both must give the oracle's bytes and codes on the adversarial set."""
+    import subprocess
+    calls = _adversarial_pairing_calls()
+    want = [oracle_c.call("pairing", c) for c in calls]
+    assert {code for code, _ in want} == {0, 1, 2, 3}
+    for c, (code, ref) in zip(calls, want):                                  # one call at a time (legacy ABI)
+        got_code, got = product.raw_call("bls12_pairing", c, 32)
+        assert got_code == code and (code != 0 or got == ref), (len(c), got_code, code)
+    offs = [0]
+    for c in calls:
+        offs.append(offs[-1] + len(c))
+    blob = b"".join(calls)
+    outs, errs = product.PairingBatch(blob, offs)                            # a small batch: same path, many blocks
+    assert [int(e) for e in errs] == [code for code, _ in want]
+    assert all(bytes(outs[j]) == (want[j][1] if want[j][0] == 0 else bytes(32)) for j in range(len(calls)))
+    path = os.path.join(ROOT, "gpurun_out", "_pair_input.bin")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as fh:
+        fh.write(blob)
+    code = ("import sys; sys.path.insert(0, %r); import blst_eip2537_b200 as b; d = open(%r, 'rb').read(); offs = %r; "
+            "outs, errs = b.PairingBatch(d, offs); print(' '.join('%%d:%%s' %% (int(e), bytes(o).hex()) for o, e in zip(outs, errs)))"
+            % (ROOT, path, offs))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, B200_PAIR_COOP_MAX="-1"), timeout=600)
+    os.remove(path)
+    assert res.returncode == 0, res.stderr
+    got = res.stdout.split()
+    assert got == ["%d:%s" % (c, (r if c == 0 else bytes(32)).hex()) for c, r in want]
+
+
+def test_opt_in_affine_pair_rounds_are_bit_exact(oracle_c):
+    """B200_AFFINE_ROUNDS=2 (batched-affine pair rounds before the XYZZ walk; opt-in, measured at break-even) must give the
+    oracle's bytes, also when buckets hold repeated points, P / -P pairs and points at infinity (every case of
+    ec.cuh pair_prepare), for G1 and G2, in a fresh process."""
+    import subprocess
+    rnd = random.Random(0x2537 + 71)
+    def adversarial(gen_mul, neg, psize, n):
+        base = [gen_mul(rnd.randrange(1, po.R)) for _ in range(6)]
+        pairs = []
+        for i in range(n):
+            pt = base[rnd.randrange(6)] if i % 3 else bytes(psize)          # few distinct points, every third at infinity
+            if i % 5 == 0 and pt != bytes(psize):
+                pt = neg(pt)
+            k = rnd.choice([1, 2, 3, 7, 255, 256, (1 << 255) + 5, po.R - 1, rnd.getrandbits(256)])
+            pairs.append(pt + k.to_bytes(32, "big"))
+        return b"".join(pairs)
+    neg1 = lambda b: po.encode_g1(po.ec_neg(po.FP_OPS, po.decode_g1(b)[1]))
+    neg2 = lambda b: po.encode_g2(po.ec_neg(po.F2_OPS, po.decode_g2(b)[1]))
+    d1 = adversarial(oracle_c.g1_gen_mul, neg1, 128, 700)
+    d2 = adversarial(oracle_c.g2_gen_mul, neg2, 256, 300)
+    big, s_big = wl.g1_msm_input((1 << 15) + 9, 0x7171)
+    want = [oracle_c.call("g1multiexp", d1), oracle_c.call("g2multiexp", d2), (0, oracle_c.g1_gen_mul(s_big))]
+    path = os.path.join(ROOT, "gpurun_out", "_affine_input.bin")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as fh:
+        fh.write(d1 + d2 + big)
+    code = ("import sys; sys.path.insert(0, %r); import blst_eip2537_b200 as b; d = open(%r, 'rb').read(); a, c = %d, %d; "
+            "print(b.raw_call('bls12_g1multiexp', d[:a], 128)[1].hex()); print(b.raw_call('bls12_g2multiexp', d[a:a + c], 256)[1].hex()); "
+            "print(b.G1Multiexp(d[a + c:]).hex())" % (ROOT, path, len(d1), len(d2)))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, B200_AFFINE_ROUNDS="2"), timeout=600)
+    os.remove(path)
+    assert res.returncode == 0, res.stderr
+    assert all(c == 0 for c, _ in want)
+    assert res.stdout.split() == [w.hex() for _, w in want]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -2,16 +2,20 @@
 # Round-2 evidence run on ONE B200 (developer tool): bench lines, launch lists, ncu captures, latency probes.
 set -x
 O=gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > $O/r02_gpu_tests.log 2>&1
 python bench.py > $O/r02_bench.json 2> $O/r02_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_ref.json 2>> $O/r02_bench.err
 python bench.py --workload pairing --pairs 2 --steps 3 --no-cpu > $O/r02_pairing_k2.json 2>> $O/r02_bench.err
 python bench.py --workload pairing --pairs 16 --steps 3 --no-cpu > $O/r02_pairing_k16.json 2>> $O/r02_bench.err
 python bench.py --logn 16 --steps 5 --no-cpu > $O/r02_g1_2p16.json 2>> $O/r02_bench.err
 python bench.py --logn 18 --steps 5 --no-cpu > $O/r02_g1_2p18.json 2>> $O/r02_bench.err
+python bench.py --logn 12 --steps 5 --no-cpu > $O/r02_g1_2p12.json 2>> $O/r02_bench.err
+for c in 1 128 1024 4096; do python bench.py --workload pairing --calls $c --steps 5 --no-cpu > $O/r02_pairing_c$c.json 2>> $O/r02_bench.err; done
 python tools/quick_bench.py single checked check batch > $O/r02_quick.log 2>&1
 python tools/quick_bench.py micro latency > $O/r02_micro.log 2>&1
 # launch lists (cold-cache, serialised: shares of the step only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_bench_launches.csv python bench.py --steps 2 --warmup 1 --secondary 0 --no-cpu > $O/r02_ncu_launch1.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/r02_g2_launches.csv python bench.py --workload g2msm --steps 1 --warmup 1 --no-cpu > $O/r02_ncu_launch3.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r02_pairing_launches.csv python bench.py --workload pairing --steps 1 --warmup 1 --no-cpu > $O/r02_ncu_launch2.log 2>&1
 # full captures of the dominant kernels
 # (the .ncu-rep files are summarised ON THE BOX and deleted: gpurun only brings back 64 MiB)
