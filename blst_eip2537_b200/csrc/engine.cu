@@ -410,6 +410,7 @@ static int msm_begin(Engine& e, MsmRun<F>& r, size_t n_total, size_t chunk_n) {
     static const int rounds_env = getenv("B200_AFFINE_ROUNDS") ? atoi(getenv("B200_AFFINE_ROUNDS")) : 0;
     r.rounds = rounds_env < 0 ? 0 : (rounds_env > 2 ? 2 : rounds_env);
   }
+  if (r.rounds && chunk_n * (size_t)plan.nwin + nbt * (((size_t)1 << r.rounds) - 1) > 0xFFFFFFFFull) r.rounds = 0;   // 32-bit offsets incl. padding
   const size_t pad_slots = r.rounds ? nbt * (((size_t)1 << r.rounds) - 1) : 0;
   if ((rc = e.entries.reserve((chunk_n * plan.nwin + pad_slots + 4) * sizeof(uint32_t)))) return rc;
   if (r.rounds) {
