@@ -163,19 +163,34 @@ B200_HD void coop12_exec_seq(Fp2* f, const Fp2* g) {
 }
 
 #ifdef __CUDACC__
-// one warp: 8 slots x 4 lanes; f, g, P in shared memory
+// one warp; f, g, P (and the scratch behind P) in shared memory.  Every Fp2 product of the operation's table is three Fp
+// products (Karatsuba: a0 b0, a1 b1, (a0 + a1)(b0 + b1)); the 3 * NP Fp products are dealt out FLAT over the 32 lanes, so
+// a general product (54) takes two rounds and a cyclotomic squaring (27) one -- the slot geometry of coop.cuh (8 slots x 4
+// lanes, one lane of four idle) needed three and two.
 template <class OP>
 __device__ __noinline__ void coop12_exec(Fp2* f, const Fp2* g, Fp2* P) {
-  const CoopGroup cg = coop_group<Fp2>();
   const int lane = threadIdx.x & 31;
+  Fp* T = reinterpret_cast<Fp*>(P + 18);          // Coop12Smem::T
 #pragma unroll 1
-  for (int base = 0; base < OP::NP; base += 8) {
-    int s = base + cg.lane;
-    bool active = s < OP::NP;
+  for (int base = 0; base < 3 * OP::NP; base += 32) {
+    const int j = base + lane;
+    const bool active = j < 3 * OP::NP;
+    const int s = active ? j / 3 : 0, part = j % 3;
     Fp2 x, y;
-    OP::operands(active ? s : 0, f, g, x, y);
-    Fp2 r = coop_product(x, y, cg);
-    if (active && cg.sub == 0) P[s] = r;
+    OP::operands(s, f, g, x, y);
+    Fp a = add(x.c0, x.c1), b = add(y.c0, y.c1);
+    coop_pick(a, part == 0, x.c0); coop_pick(b, part == 0, y.c0);
+    coop_pick(a, part == 1, x.c1); coop_pick(b, part == 1, y.c1);
+    const Fp t = coop_mul(a, b);
+    if (active) T[j] = t;
+  }
+  __syncwarp();
+  if (lane < OP::NP) {
+    const Fp t0 = T[3 * lane], t1 = T[3 * lane + 1], t2 = T[3 * lane + 2];
+    Fp2 r;
+    r.c0 = sub(t0, t1);
+    r.c1 = sub(sub(t2, t0), t1);
+    P[lane] = r;
   }
   __syncwarp();
   Fp2 o;
@@ -187,6 +202,7 @@ __device__ __noinline__ void coop12_exec(Fp2* f, const Fp2* g, Fp2* P) {
 
 struct Coop12Smem {
   Fp2 f[6], a[6], t0[6], t1[6], t2[6], g[6], P[18];
+  Fp T[54];      // the Fp products of one operation (must follow P: coop12_exec finds it there)
 };
 
 __device__ __noinline__ void c12_copy(Fp2* dst, const Fp2* src) {
