@@ -688,6 +688,18 @@ static int h2d_copy(Engine& e, unsigned char* dst, const unsigned char* src, siz
 // host-resident input: stream it in chunks, copy of chunk i+1 overlapped with accumulation of chunk i.
 // Leaves the XYZZ partial sum at dst_partial (default e.partial) and the status key in e.status (and a copy at
 // dst_status if given) -- both may be PEER pointers on another GPU --, all work queued on e.stream.
+// developer sweep: B200_STREAM_SCHEDULE=9 B200_STREAM_CUTS="0,2,6,16,32" (cut points in thirty-seconds of the input)
+static const std::vector<int>& env_cuts() {
+  static const std::vector<int> v = [] {
+    std::vector<int> r;
+    const char* e = getenv("B200_STREAM_CUTS");
+    while (e && *e) { r.push_back(atoi(e)); const char* c = strchr(e, ','); e = c ? c + 1 : nullptr; }
+    if (r.size() < 2 || r.front() != 0 || r.back() != 32) r.clear();
+    for (size_t i = 1; i < r.size(); i++) if (r[i] <= r[i - 1]) { r.clear(); break; }
+    return r;
+  }();
+  return v;
+}
 template <class F>
 static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, uint64_t index_base,
                                 XYZZ<F>* dst_partial = nullptr, unsigned long long* dst_status = nullptr) {
@@ -706,6 +718,11 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
   static const int cuts_even8[] = {0, 4, 8, 12, 16, 20, 24, 28, 32};
   static const int cuts_mid[] = {0, 4, 8, 16, 32};
   static const int cuts_one[] = {0, 32};
+  // compute-bound regime (one rank per host): four chunks 1/16, 1/8, 5/16, 1/2 -- every chunk repeats the fixed costs of the
+  // sort and of loading / storing the buckets, so fewer chunks win once the first one is small enough (measured at 2^20:
+  // 107.2 M points/s end to end against 105.7 M with round 1's six geometric chunks; profiles/r02_bench.md)
+  static const int cuts_q4[] = {0, 2, 6, 16, 32};
+  static const int cuts_q3[] = {0, 4, 16, 32};                           // 2^18 .. 2^20 pairs: three chunks (G2 2^18: 25.8 M against 23.7 M)
   // Copy-bound regime (measured on the previous streamed call of this workspace: the copies took > 40 % of the call, e.g.
   // 8 ranks sharing the host's ~186 GB/s): what follows the LAST copy is exposed, so the last chunks must be small.
   static const int sched_env = getenv("B200_STREAM_SCHEDULE") ? atoi(getenv("B200_STREAM_SCHEDULE")) : 0;   // 1 geometric, 2 symmetric
@@ -723,7 +740,10 @@ static int msm_stream_from_host(Engine& e, const unsigned char* in, size_t n, ui
   if (n >= (1u << 18)) {
     if (even_env) { cuts = cuts_even8; nchunks = 8; }
     else if (sched_env == 2 || (sched_env == 0 && e.copy_bound)) { cuts = cuts_sym; nchunks = 8; }
-    else { cuts = cuts_geo; nchunks = 6; }
+    else if (sched_env == 1) { cuts = cuts_geo; nchunks = 6; }
+    else if (sched_env == 9 && env_cuts().size() >= 2) { cuts = env_cuts().data(); nchunks = (int)env_cuts().size() - 1; }
+    else if (n >= (1u << 20)) { cuts = cuts_q4; nchunks = 4; }
+    else { cuts = cuts_q3; nchunks = 3; }
   }
   else if (n >= (1u << 16)) { cuts = cuts_mid; nchunks = 4; }
   size_t chunk_cap = 0;
