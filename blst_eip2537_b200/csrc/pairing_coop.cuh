@@ -89,7 +89,7 @@ __device__ __noinline__ void coop_line_add(G2Proj& t, const G2Affine& q, Line& l
 __global__ void __launch_bounds__(64) k_pairing_pair_coop(const uint32_t* __restrict__ raw, size_t total_pairs, Line* __restrict__ lines,
                                                           unsigned char* __restrict__ skip, int* __restrict__ status) {
   __shared__ G1Affine sp;
-  __shared__ int code1, code2, inf1, inf2;
+  __shared__ int code1, code2, inf1, inf2, dec1;      // dec1: decode-level verdict on P, never written after the first barrier
   const size_t j = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint4* src = reinterpret_cast<const uint4*>(raw + j * 96);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(64) k_pairing_pair_coop(const uint32_t* __rest
 #pragma unroll
     for (int k = 0; k < 8; k++) { uint4 v = __ldg(src + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
     code = decode_point(p, w);
-    if (lane == 0) { sp = p; code1 = code; inf1 = (code == E_SUCCESS && is_inf(p)) ? 1 : 0; }
+    if (lane == 0) { sp = p; code1 = code; dec1 = code; inf1 = (code == E_SUCCESS && is_inf(p)) ? 1 : 0; }
   } else {
     uint32_t w[64];
 #pragma unroll
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(64) k_pairing_pair_coop(const uint32_t* __rest
       if (lane == 0 && !member) code1 = E_NOT_IN_SUBGROUP;
     }
   } else if (code == E_SUCCESS && !is_inf(q)) {
-    const int c1 = code1;            // decode-level verdict on P (its membership ladder is still running on warp 0)
+    const int c1 = dec1;             // decode-level verdict on P (its membership ladder is still running on warp 0)
     if (c1 == E_SUCCESS && inf1) {
       // P = infinity: the pair contributes 1, but Q must still be in G2 -- no walk to piggyback on: exact ladder
       if (lane == 0 && !g2_in_subgroup(q)) code2 = E_NOT_IN_SUBGROUP;
