@@ -76,6 +76,29 @@ def test_g2_msm_2_16_closed_form(product, oracle_c):
     assert product.G2Multiexp(data) == oracle_c.g2_gen_mul(total)
 
 
+def test_g2_msm_2_18_closed_form_and_linearity(product, oracle_c):
+    """BASELINE configs[2] at full size: 2^18 points a_i*G2 with uniform 256-bit scalars; expected = (sum a_i k_i mod r) * G2,
+    and MSM(A ++ B) = MSM(A) + MSM(B) through G2ADD (the host path streams the two halves in different chunkings)."""
+    rng = np.random.default_rng(0x2539)
+    n = 1 << 18
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 0] &= 0x3F
+    pts = np.frombuffer(product.generator_mul(2, a), dtype=np.uint8).reshape(n, 256)
+    for i in (0, n // 3, n - 1):
+        assert bytes(pts[i]) == oracle_c.g2_gen_mul(int.from_bytes(bytes(a[i]), "big"))
+    k = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    data = np.concatenate([pts, k], axis=1).reshape(-1)
+    ai = [int.from_bytes(bytes(r), "big") for r in a]
+    ki = [int.from_bytes(bytes(r), "big") for r in k]
+    full = product.G2Multiexp(data)
+    assert full == oracle_c.g2_gen_mul(sum(x * y for x, y in zip(ai, ki)) % po.R)
+    cut = n // 2 + 12345
+    lo = product.G2Multiexp(data[:288 * cut])
+    hi = product.G2Multiexp(data[288 * cut:])
+    assert product.G2Add(lo + hi) == full
+    assert hi == oracle_c.g2_gen_mul(sum(x * y for x, y in zip(ai[cut:], ki[cut:])) % po.R)
+
+
 def test_skewed_scalars_do_not_break_bucket_accumulation(product, oracle_c):
     """All scalars equal: every point lands in the same bucket of every window."""
     n = 4096
